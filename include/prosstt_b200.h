@@ -1,0 +1,176 @@
+/* prosstt_b200.h - C ABI of the B200 (sm_100a) implementation of PROSSTT's
+ * simulation hot path.
+ *
+ * The reference (soedinglab/prosstt 1.2.0) is pure Python and has no FFI of its
+ * own; the boundary its users see is the Python module API.  Each entry point
+ * below replaces the body of one reference function (cited as
+ * prosstt/<file>:<lines>); the Python host layer in prosstt_b200/ keeps the
+ * reference signatures and calls these through ctypes.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless named h_*;
+ *  - the caller owns all buffers; nothing here allocates, frees or synchronises;
+ *  - every call is stream-ordered on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 ok, <0 invalid argument, >0 cudaError_t; message via
+ *    pst_last_error() (thread-local);
+ *  - tree positions are "packed rows": branches in tree.branches order, branch b
+ *    owns rows [row_base[b], row_base[b]+T_b); P = sum T_b.  This is also the
+ *    concatenation order of sample_density (simulation.py:454-461);
+ *  - matrices are row-major: W[P][K], H[K][G], rel/means[P][G], X[N][G];
+ *  - every random quantity is a pure function of (seed, stream tag, global
+ *    cell/row index[, gene]) through Philox4x32-10, never of thread, block,
+ *    launch shape or rank: results are bit-identical for any partition of the
+ *    cells over calls, streams or GPUs.
+ */
+#ifndef PROSSTT_B200_H
+#define PROSSTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define PST_ABI_VERSION 1
+
+/* bits of the device-side status word written by the sampling kernels */
+#define PST_FLAG_DOMAIN   1u  /* mu <= 0, non-finite, or alpha*mu+beta-1 <= 0: scipy's
+                                 "Domain error in arguments"             */
+#define PST_FLAG_ROW      2u  /* row_of_cell outside [0,P)                              */
+#define PST_FLAG_CLAMPED  4u  /* a count exceeded INT32_MAX and was clamped             */
+#define PST_FLAG_NOZONE   8u  /* pseudotime outside every timezone (pick_branch)        */
+
+/* which per-count algorithm pst_draw_counts runs */
+#define PST_SAMPLER_GAMMA_POISSON 0  /* Marsaglia-Tsang gamma, PTRS / inversion Poisson  */
+#define PST_SAMPLER_HYBRID        1  /* direct NB inversion for small means + the above  */
+
+int         pst_abi_version(void);
+const char *pst_last_error(void);
+/* number of kernels launched by this library in this process (bench "gpu_launches") */
+uint64_t    pst_launch_count(void);
+
+/* ---- counter-based draws (replace the global MT19937 of the reference) ------- */
+/* out[i] = uniform double in [0,1), 53 bits, element index = first + i.
+ * Replaces random_sample inside np.random.choice (simulation.py:464, sim_utils.py:399). */
+int pst_uniform_f64(uint64_t seed, uint32_t tag, int64_t first, int64_t n,
+                    double *out, void *stream);
+/* out[i] = loc + scale * N(0,1).  Replaces scipy.stats.norm.rvs call sites
+ * (simulation.py:409, sim_utils.py:495).  loc/scale: per-element device arrays, or NULL
+ * to use the scalars loc0/scale0. */
+int pst_normal_f64(uint64_t seed, uint32_t tag, int64_t first, int64_t n, double loc0,
+                   double scale0, const double *loc, const double *scale, double *out,
+                   void *stream);
+/* raw Philox4x32-10 words, out[4*i..4*i+3] for counter (first+i, tag, 0) - test hook */
+int pst_philox_words(uint64_t seed, uint32_t tag, int64_t first, int64_t n,
+                     uint32_t *out, void *stream);
+
+/* ---- lineage: simulation.py:21-124, 215-286; sim_utils.py:129-142, 611-640 ---- */
+/* Draws of `diffusion` (simulation.py:107-117) for nb branches x K programs, keyed
+ * by (seed, branch_id, attempt, k, t): u0~U(0,1.5), v0~N(0,0.2), eta~U(0,1),
+ * eps[t]~N(0,2/T).  Layout: u0/v0/eta [nb*K]; eps for branch j starts at
+ * eps_off[j] and is [K][T_j-1]; max_T = max_j T[j] (host copy, sizes the grid). */
+int pst_walk_draws(uint64_t seed, int32_t nb, int32_t K, int32_t max_T,
+                   const int32_t *branch_id, const int32_t *attempt, const int32_t *T,
+                   const int64_t *eps_off, double *u0, double *v0, double *eta, double *eps,
+                   void *stream);
+/* Momentum walk of every (branch, program): walk[0]=log(u0); walk[t+1]=walk[t]+v[t];
+ * v[t+1]=eta*v[t]+eps[t] as a warp-shuffle scan (affine-map scan for v, prefix sum
+ * for walk).  Writes W[(row_base[j]+t)*K + k].  Replaces simulation.py:21-124. */
+int pst_walk_scan(int32_t nb, int32_t K, const int32_t *row_base, const int32_t *T,
+                  const int64_t *eps_off, const double *u0, const double *v0,
+                  const double *eta, const double *eps, double *W, void *stream);
+/* Parent carry in topological order: for i in 0..n_order-1, child=order_child[i],
+ * W[child rows] -= (W[child first row] - W[parent last row]).  order_parent_last[i]
+ * is the packed row of the parent's last time point, or -1 for a root.
+ * Replaces sim_utils.py:129-142, 611-640. */
+int pst_walk_carry(int32_t n_order, int32_t K, const int32_t *order_row_base,
+                   const int32_t *order_T, const int32_t *order_parent_last,
+                   double *W, void *stream);
+/* rel = W[row0:row0+nrows] . H  (simulation.py:269, sim_utils.py:190-213), fused with
+ * M = exp(rel) * gene_scale (tree.py:180-183) and the per-gene maximum of rel
+ * (simulation.py:270; sim_utils.py:406-426 since exp is monotone).  Any of the
+ * outputs may be NULL.  out_rel/out_mean64/out_mean32 are indexed from row 0 of the
+ * packed table (row r goes to out[r*G..]).  out_colmax[G] must be initialised by the
+ * caller (-inf); it is max-merged. */
+int pst_rel_means(const double *W, const double *H, const double *gene_scale,
+                  int64_t row0, int64_t nrows, int32_t K, int64_t G,
+                  double *out_rel, double *out_mean64, float *out_mean32,
+                  double *out_colmax, void *stream);
+/* Number of genes whose Pearson r between columns of A[0:n] and B[0:n] is < 0
+ * (sim_utils.py:145-168, 249-251).  out_count is one int32, caller zeroes it. */
+int pst_pearson_anticorr(const double *A, const double *B, int64_t nrows, int64_t G,
+                         int32_t *out_count, void *stream);
+/* fp64 -> fp32 table conversion for means supplied by the user (tree.add_genes). */
+int pst_f64_to_f32(const double *in, int64_t n, float *out, void *stream);
+
+/* ---- samplers' index maps: simulation.py:319-548, sim_utils.py:342-403 -------- */
+/* idx[i] = searchsorted(cdf, u[i], side='right') clipped to P-1; row_of_cell = idx
+ * (packed rows are in the same order), pt[i] = pos_pt[idx]; branch[i] = pos_branch[idx].
+ * Replaces np.random.choice(p=...) + the gathers at simulation.py:464-467. */
+int pst_density_index(const double *cdf, int32_t P, const double *u, int64_t n,
+                      const int32_t *pos_pt, const int32_t *pos_branch,
+                      int32_t *row_of_cell, int64_t *pt, int32_t *branch, void *stream);
+/* pt[i] = clip(trunc(z[i]), 0, max_time-1): draw_times, simulation.py:409-413, given
+ * z = norm.rvs(loc=t, scale=std). */
+int pst_times_from_normals(const double *z, int64_t n, int32_t max_time, int64_t *pt,
+                           void *stream);
+/* pick_branch (sim_utils.py:367-403) with one uniform u[i] per cell: zone = first
+ * timezone containing pt[i]; weights density[b][pt - zone_start] (sic)
+ * over the zone's candidate branches; p = w/sum(w) (numpy summation order); legacy
+ * choice: cdf = cumsum(p)/cumsum(p)[-1], searchsorted right.  zone_lo/zone_hi [nz];
+ * cand_off[nz+1] indexes cand_branch[]; max_cand = largest candidate list (<= 64);
+ * branch_start/row_base/T are per branch [B]; density is packed [P].
+ * Outputs branch[n] (index into tree.branches) and row_of_cell[n]; a pseudotime
+ * outside every zone (the reference returns None there) sets PST_FLAG_NOZONE. */
+int pst_pick_branch(const int64_t *pt, const double *u, int64_t n, int32_t nz,
+                    const int32_t *zone_lo, const int32_t *zone_hi, const int32_t *cand_off,
+                    const int32_t *cand_branch, int32_t max_cand, const int32_t *branch_start,
+                    const int32_t *row_base, const int32_t *T, const double *density,
+                    int32_t *branch, int32_t *row_of_cell, uint32_t *flags, void *stream);
+/* row_of_cell[i] = row_base[b] + pt[i] - branch_start[b] for caller-supplied branches
+ * (draw_counts, simulation.py:634-640); out-of-range sets PST_FLAG_ROW. */
+int pst_rows_from_branch(const int64_t *pt, const int32_t *branch, int64_t n, int32_t B,
+                         const int32_t *branch_start, const int32_t *row_base,
+                         const int32_t *T, int32_t *row_of_cell, uint32_t *flags, void *stream);
+/* sample_whole_tree (simulation.py:510-513): cell first+i takes entry (first+i)/n_factor
+ * of the cover_whole_tree enumeration (cover_pt/cover_branch/cover_row [n_cover]). */
+int pst_whole_tree_index(const int32_t *cover_pt, const int32_t *cover_branch,
+                         const int32_t *cover_row, int64_t n_cover, int64_t n_factor,
+                         int64_t first, int64_t n, int64_t *pt, int32_t *branch,
+                         int32_t *row_of_cell, void *stream);
+/* scalings = exp(z) in fp64 (returned to the user) and fp32 (consumed by the draw
+ * kernel); z=NULL writes ones (scale=False).  Replaces sim_utils.py:494-498. */
+int pst_scalings(const double *z, int64_t n, double *out64, float *out32, void *stream);
+
+/* ---- count model: count_model.py:131-161 ------------------------------------- */
+/* fp64 (p, r) of get_pr_umi for mu[n_cells][G] with per-gene alpha/beta - parity hook
+ * for the parameterisation that pst_draw_counts fuses in fp32. */
+int pst_nb_params(const double *alpha, const double *beta, const double *mu,
+                  int64_t n_cells, int64_t G, double *out_p, double *out_r, void *stream);
+
+/* ---- the hot loop: draw_counts, simulation.py:602-651 ------------------------- */
+/* X[i][g] ~ NB(mean mu = means[row_of_cell[i]][g]*scaling[i],
+ *              var  alpha[g]*mu^2 + beta[g]*mu)        i in [0,n), g in [0,G)
+ * as a gamma-Poisson mixture: gamma shape r = mu/theta, scale theta = alpha*mu +
+ * (beta-1)  (== scipy nbinom(n=r, p=1/(1+theta)), count_model.py:156-161).
+ * Random numbers: Philox4x32-10 keyed by seed with counter (gene, global cell =
+ * cell0+i, draw index) - independent of how cells are split over calls/GPUs.
+ * beta_m1[g] = beta[g]-1 formed in fp64 by the caller.  X row stride is ldx
+ * elements (>= G).  flags: one uint32, OR-ed with PST_FLAG_*. */
+int pst_draw_counts(const float *means, int64_t P, int64_t G,
+                    const int32_t *row_of_cell, const float *scaling,
+                    const float *alpha, const float *beta_m1,
+                    uint64_t seed, int64_t cell0, int64_t n,
+                    int32_t *X, int64_t ldx, uint32_t *flags, int32_t sampler,
+                    void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROSSTT_B200_H */

@@ -412,3 +412,53 @@ def philox4x32_10(counter, key):
         k0 = (k0 + np.uint64(PHILOX_W0)) & mask
         k1 = (k1 + np.uint64(PHILOX_W1)) & mask
     return np.stack(c, axis=-1).astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------
+# simulate_lineage on an explicit legacy RandomState (used to build the bench tree on
+# the CPU for the reference arm, and pinned against the golden lineage fixtures)
+# ---------------------------------------------------------------------------
+def diffusion(steps, rng):
+    """simulation.py:104-124 with its draw order: U(0,1.5), N(0,.2), U(0,1), then one
+    N(0, 2/steps) per step."""
+    u0 = rng.uniform(0, 1.5)
+    v0 = rng.normal(0, 0.2)
+    eta = rng.uniform()
+    eps = np.array([rng.normal(0, 2 / steps) for _ in range(steps - 1)])
+    return diffusion_from_draws(u0, v0, eta, eps)
+
+
+def simulate_lineage(tree, rng, a=0.05, rel_exp_cutoff=8, inter_branch_tol=0):
+    """simulation.py:254-286 (gamma coefficients): H, then per BFS branch redraw until the
+    cutoff and sibling-divergence tests pass.  Returns (rel_means, programs, H)."""
+    K, G = tree.modules, tree.G
+    H = rng.standard_gamma(a, size=K * G).reshape(K, G)          # simulation.py:211
+    kids_of = {}
+    for p, c in tree.topology:
+        kids_of.setdefault(p, []).append(c)
+    W, rel = {}, {}
+    for b in bfs_branches(tree):
+        while True:
+            w = np.stack([diffusion(tree.time[b], rng) for _ in range(K)]).T
+            p = parent_of(tree, b)
+            if p is not None:
+                w = carry_from_parent(w, W[p])
+            W[b] = w
+            rel[b] = np.dot(w, H)
+            above = np.max(rel[b]) > rel_exp_cutoff
+            # find_parallel (sim_utils.py:663-667): parents in np.unique order; first
+            # sibling group containing b, restricted to branches that have programs
+            sibs = None
+            for parent in sorted(kids_of, key=lambda x: x):
+                if b in kids_of[parent]:
+                    sibs = sorted(s for s in set(kids_of[parent]) if s in W)
+                    break
+            ok = True
+            if sibs is not None and len(sibs) > 1:
+                for i in range(len(sibs) - 1):
+                    for j in range(i + 1, len(sibs)):
+                        frac = pearson_anticorrelated(rel[sibs[i]], rel[sibs[j]]) / (G * 1.0)
+                        ok = ok and (frac > inter_branch_tol)
+            if not above and ok:
+                break
+    return rel, W, H

@@ -1,0 +1,82 @@
+// Shared device helpers: Philox4x32-10, uniform/normal conversions, launch plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/prosstt_b200.h"
+
+namespace pst {
+
+// ---------------------------------------------------------------------------
+// host-side plumbing
+// ---------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+int fail_arg(const char *fn, const char *what);
+int check_launch(const char *fn);   // cudaGetLastError -> status, counts the launch
+
+#define PST_REQUIRE(cond, fn, what) do { if (!(cond)) return pst::fail_arg(fn, what); } while (0)
+
+constexpr int kNumSM = 148;          // B200: 2 dies x 74 SMs
+
+// stream tags (third Philox counter word): one independent stream per use
+enum : uint32_t {
+  TAG_WALK_U0 = 0x100, TAG_WALK_V0 = 0x101, TAG_WALK_ETA = 0x102, TAG_WALK_EPS = 0x103,
+  TAG_COUNT = 0x200,   // + draw index in the 4th counter word
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  The key schedule depends only on the seed,
+// so the ten round keys are formed once per thread and the rounds are
+// 2 x IMAD.WIDE + 2 x LOP3 each.
+// ---------------------------------------------------------------------------
+struct PhiloxKey {
+  uint32_t k0[10], k1[10];
+  __host__ __device__ explicit PhiloxKey(uint64_t seed) {
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { k0[i] = a; k1[i] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+  }
+};
+
+__device__ __forceinline__ uint4 philox(const PhiloxKey &key, uint32_t c0, uint32_t c1,
+                                        uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[i];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[i];
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// 32 random bits -> float strictly inside (0,1): (w+0.5)*2^-32, top clamped to 1-2^-24
+__device__ __forceinline__ float u01(uint32_t w) {
+  return fminf(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
+}
+// 53-bit double in [0,1) exactly as numpy's legacy random_sample builds it
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+// standard normal (fp64 Box-Muller, cosine branch) from one Philox block
+__device__ __forceinline__ double normal_f64(uint4 r) {
+  const double u1 = 1.0 - u53(r.x, r.y);          // (0,1]
+  const double u2 = u53(r.z, r.w);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
+  unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);
+  unsigned long long old = *p;
+  while (v > __longlong_as_double((long long)old)) {
+    const unsigned long long assumed = old;
+    old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+    if (old == assumed) break;
+  }
+}
+
+}  // namespace pst

@@ -1,0 +1,225 @@
+"""Device-side view of a Tree: packed tables in HBM and the count engine.
+
+Layout (include/prosstt_b200.h): branches in `tree.branches` order, branch b owns packed
+rows [row_base[b], row_base[b]+T_b); P = sum T_b.  Everything here is small and
+replicated on every GPU (a few MB; the means table is P x G fp32); only cells shard.
+"""
+import numpy as np
+import torch
+
+from prosstt_b200 import _native as nat
+
+
+class TreeTables(object):
+    """Integer maps of a tree flattened for the kernels (host numpy + device copies)."""
+
+    def __init__(self, tree, dev):
+        self.dev = dev
+        self.names = list(tree.branches)
+        self.index = {b: i for i, b in enumerate(self.names)}
+        if len(self.index) != len(self.names):
+            raise ValueError("branch names must be unique")
+        B = len(self.names)
+        self.B = B
+        self.T = np.array([int(tree.time[b]) for b in self.names], dtype=np.int32)
+        if np.any(self.T < 1):
+            raise ValueError("every branch needs at least one pseudotime step")
+        self.row_base = np.zeros(B, dtype=np.int32)
+        self.row_base[1:] = np.cumsum(self.T)[:-1]
+        self.P = int(self.T.sum())
+        bt = tree.branch_times()
+        missing = [b for b in self.names if b not in bt or len(bt[b]) != 2]
+        if missing:
+            raise ValueError("branches %s are not connected to the root by the topology" % missing)
+        self.branch_start = np.array([bt[b][0] for b in self.names], dtype=np.int32)
+        # sample_density's concatenation (simulation.py:454-461)
+        self.pos_branch = np.repeat(np.arange(B, dtype=np.int32), self.T)
+        self.pos_pt = (np.arange(self.P, dtype=np.int32) - np.repeat(self.row_base, self.T)
+                       + np.repeat(self.branch_start, self.T)).astype(np.int32)
+        # timezones and their live branches in branch_times order (sim_utils.py:274-339)
+        zones = tree.populate_timezone()
+        order = [self.index[b] for b in bt.keys() if b in self.index]
+        self.zone_lo = np.array([z[0] for z in zones], dtype=np.int32)
+        self.zone_hi = np.array([z[1] for z in zones], dtype=np.int32)
+        cand, off = [], [0]
+        for lo, hi in zones:
+            live = [b for b in order
+                    if lo >= self.branch_start[b] and hi <= self.branch_start[b] + self.T[b] - 1]
+            cand.extend(live)
+            off.append(len(cand))
+        self.cand_branch = np.array(cand, dtype=np.int32)
+        self.cand_off = np.array(off, dtype=np.int32)
+        self.max_cand = int(np.max(np.diff(self.cand_off))) if len(zones) else 0
+        # cover_whole_tree (simulation.py:520-548): zone-major, branch, time
+        cpt, cbr = [], []
+        for z, (lo, hi) in enumerate(zones):
+            for b in self.cand_branch[self.cand_off[z]:self.cand_off[z + 1]]:
+                cpt.append(np.arange(lo, hi + 1, dtype=np.int32))
+                cbr.append(np.full(hi + 1 - lo, b, dtype=np.int32))
+        self.cover_pt = np.concatenate(cpt) if cpt else np.zeros(0, np.int32)
+        self.cover_branch = np.concatenate(cbr) if cbr else np.zeros(0, np.int32)
+        self.cover_row = (self.row_base[self.cover_branch] + self.cover_pt
+                          - self.branch_start[self.cover_branch]).astype(np.int32)
+        self.max_time = int((self.branch_start + self.T).max())
+        self._dev = {}
+
+    def d(self, name, dtype=torch.int32):
+        """Device copy of one of the host tables (cached)."""
+        if name not in self._dev:
+            self._dev[name] = nat.to_dev(getattr(self, name), dtype, self.dev)
+        return self._dev[name]
+
+    def density_packed(self, tree):
+        dens = [np.asarray(tree.density[b], dtype=np.float64) for b in self.names]
+        for b, v in zip(self.names, dens):
+            if v.shape != (int(tree.time[b]),):
+                raise ValueError("density of branch %s has shape %s, expected (%d,)"
+                                 % (str(b), str(v.shape), int(tree.time[b])))
+        return np.concatenate(dens)
+
+    def branch_codes(self, branches):
+        """Branch names (any iterable) -> int32 indices into tree.branches."""
+        arr = np.asarray(branches)
+        if arr.dtype.kind in "iu" and all(isinstance(b, (int, np.integer)) for b in self.names):
+            lut_keys = np.array(self.names, dtype=np.int64)
+            sorter = np.argsort(lut_keys)
+            pos = np.searchsorted(lut_keys, arr, sorter=sorter)
+            pos = np.clip(pos, 0, len(lut_keys) - 1)
+            codes = sorter[pos]
+            if np.any(lut_keys[codes] != arr):
+                raise KeyError("unknown branch name in `branches`")
+            return codes.astype(np.int32)
+        try:
+            return np.array([self.index[b.item() if hasattr(b, "item") else b] for b in arr],
+                            dtype=np.int32)
+        except KeyError as err:
+            raise KeyError("unknown branch name in `branches`: %s" % err)
+
+    def branch_names(self, codes):
+        """int32 indices -> array of branch names with the dtype numpy gives the names
+        (reference: possible_branches[sample], simulation.py:461-467)."""
+        return np.array(self.names)[np.asarray(codes, dtype=np.int64)]
+
+
+def choice_cdf(p):
+    """The cdf numpy's legacy RandomState.choice builds (with its validity checks)."""
+    p = np.asarray(p, dtype=np.float64)
+    if p.ndim != 1 or p.size == 0:
+        raise ValueError("'p' must be 1-dimensional and non-empty")
+    if np.any(np.isnan(p)) or np.any(p < 0):
+        raise ValueError("probabilities are not non-negative")
+    if abs(float(np.sum(p)) - 1.0) > np.sqrt(np.finfo(np.float64).eps):
+        raise ValueError("probabilities do not sum to 1")
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    return cdf
+
+
+def means_table(tree, tables, dev):
+    """(P, G) fp32 means table in HBM, built once per tree.means and cached on the tree."""
+    if tree.means is None:
+        raise ValueError("the tree has no mean expression yet: call add_genes() or "
+                         "default_gene_expression() first")
+    key = ("means32", str(dev), id(tree.means)) + tuple(id(tree.means[b]) for b in tables.names)
+    cache = tree.__dict__.setdefault("_device_cache", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    G = int(tree.G)
+    out = torch.empty((tables.P, G), dtype=torch.float32, device=dev)
+    st = nat.stream_ptr(dev)
+    for i, b in enumerate(tables.names):
+        m = tree.means[b]
+        if isinstance(m, torch.Tensor):
+            m64 = m.to(device=dev, dtype=torch.float64).contiguous()
+        else:
+            m64 = nat.to_dev(m, torch.float64, dev)
+        if tuple(m64.shape) != (int(tables.T[i]), G):
+            raise ValueError("means of branch %s have shape %s, expected %s"
+                             % (str(b), tuple(m64.shape), (int(tables.T[i]), G)))
+        dst = out[int(tables.row_base[i]):int(tables.row_base[i]) + int(tables.T[i])]
+        nat.call("pst_f64_to_f32", nat.ptr(m64), m64.numel(), dst.data_ptr(), st)
+    cache.clear()
+    cache[key] = out
+    return out
+
+
+def gene_params(alpha, beta, G, dev):
+    """Per-gene alpha and beta-1 as fp32 device vectors (beta-1 formed in fp64)."""
+    a = np.broadcast_to(np.asarray(alpha, dtype=np.float64), (G,)) if np.ndim(alpha) == 0 \
+        else np.asarray(alpha, dtype=np.float64)
+    b = np.broadcast_to(np.asarray(beta, dtype=np.float64), (G,)) if np.ndim(beta) == 0 \
+        else np.asarray(beta, dtype=np.float64)
+    if a.shape != (G,) or b.shape != (G,):
+        raise ValueError("alpha and beta must be scalars or have one value per gene (G=%d)" % G)
+    return nat.to_dev(a, torch.float32, dev), nat.to_dev(b - 1.0, torch.float32, dev)
+
+
+def raise_flags(word):
+    """Translate the device status word into the reference's exceptions."""
+    if word & nat.FLAG_ROW:
+        raise IndexError("a cell's pseudotime lies outside its branch")
+    if word & nat.FLAG_NOZONE:
+        raise IndexError("a pseudotime value lies outside the lineage tree")
+    if word & nat.FLAG_DOMAIN:
+        raise ValueError("Domain error in arguments. The mean expression must be positive "
+                         "and alpha*mean + beta must exceed 1 for every cell and gene.")
+    if word & nat.FLAG_CLAMPED:
+        raise OverflowError("a sampled count exceeded the int32 range")
+
+
+class CountEngine(object):
+    """draw_counts on one GPU: replicated small state + a cell range to sample."""
+
+    def __init__(self, tree, tables, alpha, beta, dev, sampler="gamma_poisson"):
+        self.dev = dev
+        self.G = int(tree.G)
+        self.P = tables.P
+        self.means = means_table(tree, tables, dev)
+        self.alpha, self.beta_m1 = gene_params(alpha, beta, self.G, dev)
+        self.sampler = nat.SAMPLERS[sampler]
+        self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def draw(self, rows, scaling32, seed, cell0, out=None):
+        """Sample X for the cells described by rows/scaling32 (device tensors); global
+        index of the first cell is cell0.  Returns an (n, G) int32 device tensor."""
+        n = int(rows.numel())
+        if out is None:
+            out = torch.empty((n, self.G), dtype=torch.int32, device=self.dev)
+        nat.call("pst_draw_counts", nat.ptr(self.means), self.P, self.G, nat.ptr(rows),
+                 nat.ptr(scaling32), nat.ptr(self.alpha), nat.ptr(self.beta_m1),
+                 seed, int(cell0), n, out.data_ptr(), out.stride(0) if n else self.G,
+                 nat.ptr(self.flags), self.sampler, nat.stream_ptr(self.dev))
+        return out
+
+    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None):
+        """Sample in cell chunks and stream them into `host_out` (an (n, G) int32 CPU
+        tensor, ideally pinned): sampling of chunk i+1 overlaps the copy of chunk i."""
+        n = int(rows.numel())
+        if chunk_cells is None:
+            chunk_cells = max(1, min(n, (256 << 20) // max(1, 4 * self.G)))
+        bufs = [torch.empty((chunk_cells, self.G), dtype=torch.int32, device=self.dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=self.dev)
+        main = torch.cuda.current_stream(self.dev)
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for i, lo in enumerate(range(0, n, chunk_cells)):
+            hi = min(n, lo + chunk_cells)
+            buf = bufs[i & 1][:hi - lo]
+            if i >= 2:
+                main.wait_event(free[i & 1])
+            self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=buf)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                host_out[lo:hi].copy_(buf, non_blocking=True)
+                free[i & 1].record(copy_stream)
+        copy_stream.synchronize()
+        return host_out
+
+    def check(self):
+        """One device->host read of the status word; raises like the reference would."""
+        word = int(self.flags.item())
+        if word:
+            self.flags.zero_()
+            raise_flags(word)

@@ -1,0 +1,437 @@
+"""Simulation entry points: lineage (mean expression along the tree) and the three cell
+samplers with their negative-binomial count draw.
+
+Mirror of prosstt/simulation.py (same names, arguments, defaults, return tuples and
+exceptions); the numeric work is done by the sm_100a kernels behind include/prosstt_b200.h.
+Extra keyword-only arguments (never required):
+
+  seed     64-bit key of the counter-based generator; None draws it from the global
+           legacy numpy stream, so `np.random.seed(s)` makes a script reproducible
+  device   CUDA device (default: current)
+  shard    (rank, world): sample only this rank's contiguous slice of the cells; every
+           random quantity is keyed by the GLOBAL cell index, so the union over ranks is
+           bit-identical to the unsharded call
+  dtype    dtype of the returned count matrix (reference: int64; int32 avoids a host pass)
+  out      "numpy" (reference behaviour) or "torch" (leave everything on the GPU)
+  sampler  "gamma_poisson" or "hybrid" 
+"""
+import warnings
+
+import numpy as np
+import pandas as pd
+import torch
+
+from prosstt_b200 import _native as nat
+from prosstt_b200 import count_model as cm
+from prosstt_b200 import sim_utils as sut
+from prosstt_b200.device import CountEngine, TreeTables, choice_cdf, raise_flags
+
+DEFAULT_SAMPLER = "gamma_poisson"
+
+
+# =============================================================================== lineage
+def _walk_programs(lengths, K, seed, branch_ids, attempts, dev, draws=None):
+    """Raw (un-carried) momentum walks of several branches: packed (sum T, K) device
+    tensor.  `draws` = (u0, v0, eta, eps) host arrays replace the Philox draws."""
+    nb = len(lengths)
+    T = np.asarray(lengths, dtype=np.int32)
+    row_base = np.zeros(nb, dtype=np.int32)
+    row_base[1:] = np.cumsum(T)[:-1]
+    eps_off = np.zeros(nb + 1, dtype=np.int64)
+    eps_off[1:] = np.cumsum((T.astype(np.int64) - 1) * K)
+    st = nat.stream_ptr(dev)
+    d_T = nat.to_dev(T, torch.int32, dev)
+    d_off = nat.to_dev(eps_off, torch.int64, dev)
+    if draws is None:
+        u0 = torch.empty(nb * K, dtype=torch.float64, device=dev)
+        v0 = torch.empty_like(u0)
+        eta = torch.empty_like(u0)
+        eps = torch.empty(max(1, int(eps_off[-1])), dtype=torch.float64, device=dev)
+        nat.call("pst_walk_draws", seed, nb, K, int(T.max()), nat.to_dev(branch_ids, torch.int32, dev),
+                 nat.to_dev(attempts, torch.int32, dev), nat.ptr(d_T), nat.ptr(d_off),
+                 nat.ptr(u0), nat.ptr(v0), nat.ptr(eta), nat.ptr(eps), st)
+    else:
+        u0, v0, eta = (nat.to_dev(np.ravel(x), torch.float64, dev) for x in draws[:3])
+        flat = np.concatenate([np.ravel(e) for e in draws[3]]) if len(draws[3]) else np.zeros(0)
+        eps = nat.to_dev(flat if flat.size else np.zeros(1), torch.float64, dev)
+    W = torch.empty((int(T.sum()), K), dtype=torch.float64, device=dev)
+    nat.call("pst_walk_scan", nb, K, nat.to_dev(row_base, torch.int32, dev), nat.ptr(d_T),
+             nat.ptr(d_off), nat.ptr(u0), nat.ptr(v0), nat.ptr(eta), nat.ptr(eps), nat.ptr(W), st)
+    return W
+
+
+def diffusion(steps, seed=None, device=None):
+    """One momentum random walk of `steps` points (simulation.py:89-124):
+    walk[0]=log U(0,1.5), v[0]~N(0,.2), eta~U(0,1), v[t+1]=eta v[t]+N(0,2/steps),
+    walk[t+1]=walk[t]+v[t]."""
+    dev = nat.device(device)
+    W = _walk_programs([steps], 1, nat.split_seed(seed), [0], [0], dev)
+    return W[:, 0].cpu().numpy()
+
+
+def sim_expr_branch(branch_length, expr_progr, cutoff=0.2, max_loops=100, seed=None, device=None):
+    """K = expr_progr walks of one branch as a (T, K) array (simulation.py:21-86).  The
+    reference's correlation rejection never triggers; cutoff/max_loops are
+    accepted and ignored."""
+    dev = nat.device(device)
+    W = _walk_programs([branch_length], expr_progr, nat.split_seed(seed), [0], [0], dev)
+    return W.cpu().numpy()
+
+
+def _sim_coeff_gamma(tree, a=0.05):
+    """H[k,g] ~ Gamma(a, 1), shape (K, G) (simulation.py:192-212); global legacy stream."""
+    return np.random.standard_gamma(a, size=tree.modules * tree.G).reshape((tree.modules, tree.G))
+
+
+def _sim_coeff_beta(tree, groups, a=2, b=2):
+    """H[k,g] += Beta(a,b) for each membership of gene g in program k
+    (simulation.py:164-189)."""
+    H = np.zeros((tree.modules, tree.G))
+    for k in range(tree.modules):
+        for gene in groups[k]:
+            H[k][gene] += np.random.beta(a, b)
+    return H
+
+
+def simulate_coefficients(tree, fallback_a=0.04, **kwargs):
+    """Program -> gene weights H (simulation.py:127-161): no 'a' -> warn, Gamma(0.04);
+    'a' and 'b' -> Beta(2,2) over random groups (the values are ignored);
+    'a' only -> Gamma(a)."""
+    if "a" not in kwargs:
+        warnings.warn("No argument 'a' specified in kwargs: using gamma and a=0.04", UserWarning)
+        return _sim_coeff_gamma(tree, fallback_a)
+    if "b" in kwargs:
+        return _sim_coeff_beta(tree, sut.create_groups(tree.modules, tree.G))
+    return _sim_coeff_gamma(tree, a=kwargs["a"])
+
+
+class _LineageState(object):
+    """Device buffers of simulate_lineage: packed W (P,K) and rel (P,G) in fp64."""
+
+    def __init__(self, tree, H, dev):
+        self.dev = dev
+        self.tables = TreeTables(tree, dev)
+        self.K, self.G = int(tree.modules), int(tree.G)
+        self.H = nat.to_dev(H, torch.float64, dev)
+        P = self.tables.P
+        self.W = torch.zeros((P, max(1, self.K)), dtype=torch.float64, device=dev)
+        self.rel = torch.empty((P, self.G), dtype=torch.float64, device=dev)
+        self.colmax = torch.empty(self.G, dtype=torch.float64, device=dev)
+        top = tree.topology
+        self.parent = {}
+        for p, c in top:
+            self.parent.setdefault(c, p)             # first row wins (sim_utils.py:632-635)
+
+    def rows(self, b):
+        i = self.tables.index[b]
+        lo = int(self.tables.row_base[i])
+        return lo, lo + int(self.tables.T[i])
+
+    def place_branch(self, b, raw):
+        """Copy a raw (T,K) walk in, carry the parent's end point, form rel rows and the
+        maximum relative expression of the branch.  Returns that maximum (host float)."""
+        st = nat.stream_ptr(self.dev)
+        lo, hi = self.rows(b)
+        K, G = self.K, self.G
+        if K > 0:
+            self.W[lo:hi].copy_(raw)
+            p = self.parent.get(b)
+            if p is not None:
+                plo, phi = self.rows(p)
+                order = torch.tensor([lo, hi - lo, phi - 1], dtype=torch.int32, device=self.dev)
+                nat.call("pst_walk_carry", 1, K, order[0:1].data_ptr(), order[1:2].data_ptr(),
+                         order[2:3].data_ptr(), nat.ptr(self.W), st)
+        self.colmax.fill_(float("-inf"))
+        nat.call("pst_rel_means", nat.ptr(self.W), nat.ptr(self.H), None, lo, hi - lo, K, G,
+                 nat.ptr(self.rel), None, None, nat.ptr(self.colmax), st)
+        return float(self.colmax.max().item())
+
+
+def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_tol=0,
+                     seed=None, device=None, max_attempts=10000, **kwargs):
+    """Relative mean expression of every gene at every tree position
+    (simulation.py:215-286).  Branches are visited breadth first; each gets K momentum
+    walks (device scan), is shifted to start where its parent ended, and rel = W.H is
+    formed; the branch is redrawn while its largest relative expression exceeds
+    rel_exp_cutoff or some pair of already simulated siblings has no more than
+    inter_branch_tol of its genes anticorrelated.
+
+    Returns (pd.Series rel_means, pd.Series programs, H), indexed in visiting order."""
+    if not len(tree.time) == tree.num_branches:
+        raise ValueError("the parameters are not enough for %i branches" % tree.num_branches)
+    dev = nat.device(device)
+    H = simulate_coefficients(tree, **kwargs)
+    walk_seed = nat.split_seed(seed)
+    state = _LineageState(tree, H, dev)
+    tables = state.tables
+    K = state.K
+    done = {}                                   # branch -> rel rows view (device)
+    for branch in sut.breadth_first_branches(tree):
+        b = branch.item() if hasattr(branch, "item") else branch
+        bi = tables.index[b]
+        lo, hi = state.rows(b)
+        attempt = 0
+        while True:
+            if attempt >= max_attempts:
+                raise RuntimeError("branch %s: no acceptable expression programs after %d "
+                                   "attempts (rel_exp_cutoff=%g, inter_branch_tol=%g)"
+                                   % (str(b), attempt, rel_exp_cutoff, inter_branch_tol))
+            raw = _walk_programs([hi - lo], K, walk_seed, [bi], [attempt], dev) if K > 0 else None
+            top = state.place_branch(b, raw)
+            attempt += 1
+            if top > rel_exp_cutoff:                                   # simulation.py:270
+                continue
+            done[b] = state.rel[lo:hi]
+            parallels = sut.find_parallel(tree, done, b)               # :271
+            parallels = [p.item() if hasattr(p, "item") else p for p in parallels]
+            diverges = sut.diverging_parallel(parallels, done, tree.G, tol=inter_branch_tol,
+                                              device=dev)              # :272
+            if all(diverges):
+                break
+            del done[b]
+    rel_host = state.rel.cpu().numpy()
+    W_host = state.W.cpu().numpy()[:, :K]
+    rel_means, programs = {}, {}
+    for branch in sut.breadth_first_branches(tree):
+        b = branch.item() if hasattr(branch, "item") else branch
+        lo, hi = state.rows(b)
+        rel_means[branch] = rel_host[lo:hi]
+        programs[branch] = W_host[lo:hi]
+    return pd.Series(rel_means), pd.Series(programs), H
+
+
+# =============================================================================== samplers
+def _shard_range(n, shard):
+    if shard is None:
+        return 0, n
+    rank, world = shard
+    if not (0 <= rank < world):
+        raise ValueError("shard must be (rank, world) with 0 <= rank < world")
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def _finish(engine, tables, X, pt, codes, s64, dtype, out):
+    engine.check()
+    if out == "torch":
+        return X, pt, codes, s64
+    Xh = X.cpu().numpy()
+    if np.dtype(dtype) != Xh.dtype:
+        Xh = Xh.astype(dtype)
+    return Xh, pt.cpu().numpy(), tables.branch_names(codes.cpu().numpy()), s64.cpu().numpy()
+
+
+def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
+                    seed, first, dev, dtype, out, sampler):
+    """Common tail of every sampler (simulation.py:590-599): scalings, then counts."""
+    n = int(rows.numel())
+    s64, s32 = sut.calc_scalings(n, scale, scale_mean, scale_v, seed=nat.derive_seed(seed, 1),
+                                 first=first, device=dev, return_device=True)
+    engine = CountEngine(tree, tables, alpha, beta, dev, sampler=sampler)
+    X = engine.draw(rows, s32, nat.derive_seed(seed, 2), first)
+    return _finish(engine, tables, X, pt, codes, s64, dtype, out)
+
+
+def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, scale_mean=0.,
+                   seed=None, device=None, shard=None, dtype=np.int64, out="numpy",
+                   sampler=DEFAULT_SAMPLER, uniforms=None):
+    """Sample `no_cells` (pseudotime, branch) pairs according to tree.density and draw
+    their counts (simulation.py:416-471).  Returns (X, pseudotime, branches, scalings).
+    `uniforms` (one per cell) replays externally supplied draws through the index map."""
+    dev = nat.device(device)
+    seed = nat.split_seed(seed)
+    tables = TreeTables(tree, dev)
+    cdf = nat.to_dev(choice_cdf(tables.density_packed(tree)), torch.float64, dev)
+    lo, hi = _shard_range(int(no_cells), shard)
+    n = hi - lo
+    st = nat.stream_ptr(dev)
+    if uniforms is None:
+        u = torch.empty(n, dtype=torch.float64, device=dev)
+        nat.call("pst_uniform_f64", nat.derive_seed(seed, 0), nat.TAG_DENSITY_U, lo, n, nat.ptr(u), st)
+    else:
+        u = nat.to_dev(np.asarray(uniforms)[lo:hi], torch.float64, dev)
+    rows = torch.empty(n, dtype=torch.int32, device=dev)
+    pt = torch.empty(n, dtype=torch.int64, device=dev)
+    codes = torch.empty(n, dtype=torch.int32, device=dev)
+    nat.call("pst_density_index", nat.ptr(cdf), tables.P, nat.ptr(u), n, nat.ptr(tables.d("pos_pt")),
+             nat.ptr(tables.d("pos_branch")), nat.ptr(rows), nat.ptr(pt), nat.ptr(codes), st)
+    return _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
+                           seed, lo, dev, dtype, out, sampler)
+
+
+def cover_whole_tree(tree):
+    """All (pseudotime, branch) pairs of the tree: timezone-major, then branch, then time
+    (simulation.py:520-548)."""
+    zones = tree.populate_timezone()
+    live = sut.assign_branches(tree.branch_times(), zones)
+    pseudotime, branches = [], []
+    for i, (lo, hi) in enumerate(zones):
+        for branch in live[i]:
+            pseudotime.extend(range(lo, hi + 1))
+            branches.extend([branch] * (hi + 1 - lo))
+    return pseudotime, branches
+
+
+def sample_whole_tree(tree, n_factor, alpha=0.3, beta=2, scale=True, scale_mean=0., scale_v=0.7,
+                      seed=None, device=None, shard=None, dtype=np.int64, out="numpy",
+                      sampler=DEFAULT_SAMPLER):
+    """Every tree position sampled n_factor times (simulation.py:474-517)."""
+    dev = nat.device(device)
+    seed = nat.split_seed(seed)
+    tables = TreeTables(tree, dev)
+    total = len(tables.cover_pt) * int(n_factor)
+    lo, hi = _shard_range(total, shard)
+    n = hi - lo
+    rows = torch.empty(n, dtype=torch.int32, device=dev)
+    pt = torch.empty(n, dtype=torch.int64, device=dev)
+    codes = torch.empty(n, dtype=torch.int32, device=dev)
+    nat.call("pst_whole_tree_index", nat.ptr(tables.d("cover_pt")), nat.ptr(tables.d("cover_branch")),
+             nat.ptr(tables.d("cover_row")), len(tables.cover_pt), int(n_factor), lo, n,
+             nat.ptr(pt), nat.ptr(codes), nat.ptr(rows), nat.stream_ptr(dev))
+    return _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
+                           seed, lo, dev, dtype, out, sampler)
+
+
+def draw_times(timepoint, no_cells, max_time, var=4, seed=None, first=0, device=None,
+               return_device=False, normals=None):
+    """Pseudotimes around a sample point: N(timepoint, var) truncated toward zero and
+    clipped to [0, max_time-1] (simulation.py:382-413; `var` is used as a std)."""
+    dev = nat.device(device)
+    st = nat.stream_ptr(dev)
+    if normals is None:
+        z = torch.empty(no_cells, dtype=torch.float64, device=dev)
+        nat.call("pst_normal_f64", nat.split_seed(seed), nat.TAG_SERIES_Z, int(first), no_cells,
+                 float(timepoint), float(var), None, None, nat.ptr(z), st)
+    else:
+        z = nat.to_dev(normals, torch.float64, dev)
+    pt = torch.empty(no_cells, dtype=torch.int64, device=dev)
+    nat.call("pst_times_from_normals", nat.ptr(z), no_cells, int(max_time), nat.ptr(pt), st)
+    return pt if return_device else pt.cpu().numpy()
+
+
+def sample_pseudotime_series(tree, cells, series_points, point_std, alpha=0.3, beta=2, scale=True,
+                             scale_mean=0, scale_v=0.7, seed=None, device=None, shard=None,
+                             dtype=np.int64, out="numpy", sampler=DEFAULT_SAMPLER):
+    """Time-series experiment: normally distributed pseudotimes around each sample point,
+    branches picked by density (simulation.py:319-379)."""
+    dev = nat.device(device)
+    seed = nat.split_seed(seed)
+    series_points, cells, point_std = sut.process_timeseries_input(series_points, cells, point_std)
+    max_time = tree.get_max_time()
+    total = int(np.sum(cells))
+    lo, hi = _shard_range(total, shard)
+    # per-cell loc/scale of the global cell range [lo, hi)
+    loc = np.repeat(np.asarray(series_points, dtype=np.float64), cells)[lo:hi]
+    std = np.repeat(np.asarray(point_std, dtype=np.float64), cells)[lo:hi]
+    n = hi - lo
+    st = nat.stream_ptr(dev)
+    z = torch.empty(n, dtype=torch.float64, device=dev)
+    nat.call("pst_normal_f64", nat.derive_seed(seed, 0), nat.TAG_SERIES_Z, lo, n, 0.0, 1.0,
+             nat.to_dev(loc, torch.float64, dev), nat.to_dev(std, torch.float64, dev),
+             nat.ptr(z), st)
+    pt = torch.empty(n, dtype=torch.int64, device=dev)
+    if n:
+        nat.call("pst_times_from_normals", nat.ptr(z), n, int(max_time), nat.ptr(pt), st)
+    return _sample_data_at_times(tree, pt, alpha=alpha, beta=beta, scale=scale, scale_mean=scale_mean,
+                                 scale_v=scale_v, seed=nat.derive_seed(seed, 3), device=dev,
+                                 dtype=dtype, out=out, sampler=sampler, _first=lo)
+
+
+def sample_whole_tree_restricted(tree, alpha=0.2, beta=3, seed=None, device=None, dtype=np.int64,
+                                 out="numpy", sampler=DEFAULT_SAMPLER):
+    """Bare-bones run with default lineage parameters (simulation.py:289-316): one cell
+    per pseudotime value, random branch, per-gene alpha/beta around the given means."""
+    sample_time = np.arange(0, tree.get_max_time())
+    tree.default_gene_expression()
+    alphas, betas = cm.generate_negbin_params(tree, mean_alpha=alpha, mean_beta=beta)
+    return _sample_data_at_times(tree, sample_time, alpha=alphas, beta=betas, seed=seed,
+                                 device=device, dtype=dtype, out=out, sampler=sampler)
+
+
+def _sample_data_at_times(tree, sample_pt, branches=None, alpha=0.3, beta=2, scale=True,
+                          scale_mean=0., scale_v=0.7, seed=None, device=None, dtype=np.int64,
+                          out="numpy", sampler=DEFAULT_SAMPLER, _first=0):
+    """Cells at given pseudotimes (simulation.py:551-599): pick branches if they are not
+    supplied, draw library sizes, draw counts.  `_first` is the global index of the first
+    cell (sharded callers)."""
+    dev = nat.device(device)
+    seed = nat.split_seed(seed)
+    tables = TreeTables(tree, dev)
+    pt = sample_pt if isinstance(sample_pt, torch.Tensor) else \
+        nat.to_dev(np.asarray(sample_pt), torch.int64, dev)
+    n = int(pt.numel())
+    if branches is None:
+        codes, rows = sut._pick_branch_codes(tree, pt, nat.derive_seed(seed, 0), _first, dev,
+                                             tables=tables)
+    else:
+        codes, rows = _rows_for(tables, pt, branches, dev)
+    return _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
+                           seed, _first, dev, dtype, out, sampler)
+
+
+def _rows_for(tables, pt, branches, dev):
+    codes = branches if isinstance(branches, torch.Tensor) else \
+        nat.to_dev(tables.branch_codes(branches), torch.int32, dev)
+    n = int(pt.numel())
+    if int(codes.numel()) != n:
+        raise ValueError("pseudotime and branches must have the same length")
+    rows = torch.empty(n, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    nat.call("pst_rows_from_branch", nat.ptr(pt), nat.ptr(codes), n, tables.B,
+             nat.ptr(tables.d("branch_start")), nat.ptr(tables.d("row_base")), nat.ptr(tables.d("T")),
+             nat.ptr(rows), nat.ptr(flags), nat.stream_ptr(dev))
+    word = int(flags.item())
+    if word:
+        raise_flags(word)
+    return codes, rows
+
+
+def draw_counts(tree, pseudotime, branches, scalings, alpha, beta, seed=None, device=None,
+                dtype=np.int64, out="numpy", sampler=DEFAULT_SAMPLER, first=0):
+    """UMI counts of cells at (pseudotime, branch) with library sizes `scalings`
+    (simulation.py:602-651): X[n,g] ~ NB(mean = means[branch_n][t_n - start, g]*scaling_n,
+    variance = alpha_g mean^2 + beta_g mean)."""
+    dev = nat.device(device)
+    seed = nat.split_seed(seed)
+    tables = TreeTables(tree, dev)
+    pt = pseudotime if isinstance(pseudotime, torch.Tensor) else \
+        nat.to_dev(np.asarray(pseudotime), torch.int64, dev)
+    codes, rows = _rows_for(tables, pt, branches, dev)
+    s32 = nat.to_dev(scalings, torch.float32, dev)
+    if np.ndim(alpha) == 0:
+        alpha = [alpha] * tree.G
+    if np.ndim(beta) == 0:
+        beta = [beta] * tree.G
+    engine = CountEngine(tree, tables, alpha, beta, dev, sampler=sampler)
+    X = engine.draw(rows, s32, seed, first)
+    engine.check()
+    if out == "torch":
+        return X
+    Xh = X.cpu().numpy()
+    return Xh if np.dtype(dtype) == Xh.dtype else Xh.astype(dtype)
+
+
+def add_non_diff_genes(inform_expr_matrix, genes, gene_params, cell_scalings, seed=None,
+                       device=None, sampler=DEFAULT_SAMPLER):
+    """Append `genes` constant-mean genes (mu = scaling * base_expr) to a count matrix
+    (simulation.py:654-675): the same NB kernel on a one-row means table."""
+    dev = nat.device(device)
+    X0 = np.asarray(inform_expr_matrix)
+    N, G = X0.shape
+    base = np.asarray(gene_params["base_expr"], dtype=np.float64).reshape(1, genes)
+
+    class _Flat(object):
+        pass
+    flat = _Flat()
+    flat.G, flat.means, flat._device_cache = genes, {0: base}, {}
+    tables = _Flat()
+    tables.names, tables.P = [0], 1
+    tables.T, tables.row_base = np.array([1], np.int32), np.array([0], np.int32)
+    engine = CountEngine(flat, tables, gene_params["alpha"], gene_params["beta"], dev, sampler=sampler)
+    rows = torch.zeros(N, dtype=torch.int32, device=dev)
+    s32 = nat.to_dev(cell_scalings, torch.float32, dev)
+    extra = engine.draw(rows, s32, nat.split_seed(seed), 0)
+    engine.check()
+    fusion = np.zeros((N, G + genes))
+    fusion[:, :G] = X0
+    fusion[:, G:] = extra.cpu().numpy()
+    return fusion

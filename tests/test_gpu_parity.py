@@ -1,0 +1,459 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python API) with the
+oracle and with the fixtures produced by running the reference.  Needs a GPU.
+
+Bars (BASELINE.json north_star):
+  * deterministic stages given the reference's draws: rel 1e-6 in fp64 (we assert 1e-11),
+    1e-5 where fp32 is used (the fp32 means table; we assert 2e-7);
+  * cell -> (branch, pseudotime) index maps: bit-exact;
+  * counts: in distribution (per-gene mean/variance z-scores, chi-square against the NB pmf,
+    two-sample test against numpy's legacy negative_binomial on the same parameters);
+  * counts bit-exact across cell partitions.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_lineage, load_npz
+from oracle import prosstt_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+from prosstt_b200 import _native as nat  # noqa: E402
+from prosstt_b200 import count_model as cm, sim_utils as sut, simulation as sim, tree as ptree  # noqa: E402
+from prosstt_b200.device import CountEngine, TreeTables  # noqa: E402
+
+DEV = "cuda:0"
+SAMPLERS = ["gamma_poisson"]
+
+
+def _dev(a, dtype):
+    return nat.to_dev(a, dtype, torch.device(DEV))
+
+
+# ------------------------------------------------------------------ generator
+def test_philox_words_bit_exact():
+    n, first, seed, tag = 1000, (1 << 33) + 5, 0x0123456789ABCDEF, 7
+    out = torch.empty(4 * n, dtype=torch.int32, device=DEV)
+    nat.call("pst_philox_words", seed, tag, first, n, nat.ptr(out), nat.stream_ptr(torch.device(DEV)))
+    got = out.cpu().numpy().view(np.uint32).reshape(n, 4)
+    idx = first + np.arange(n, dtype=np.uint64)
+    ctr = np.stack([(idx & 0xFFFFFFFF), (idx >> 32), np.full(n, tag), np.zeros(n)], axis=1).astype(np.uint32)
+    key = np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32)
+    want = orc.philox4x32_10(ctr, np.broadcast_to(key, (n, 2)))
+    assert np.array_equal(got, want)
+
+
+def test_uniform_and_normal_streams():
+    n = 200000
+    dev = torch.device(DEV)
+    u = torch.empty(n, dtype=torch.float64, device=dev)
+    nat.call("pst_uniform_f64", 5, 1, 0, n, nat.ptr(u), nat.stream_ptr(dev))
+    # offset invariance: elements [1000, 2000) of the same stream
+    u2 = torch.empty(1000, dtype=torch.float64, device=dev)
+    nat.call("pst_uniform_f64", 5, 1, 1000, 1000, nat.ptr(u2), nat.stream_ptr(dev))
+    assert torch.equal(u[1000:2000], u2)
+    uh = u.cpu().numpy()
+    assert 0 <= uh.min() and uh.max() < 1 and abs(uh.mean() - 0.5) < 4 * np.sqrt(1 / 12 / n)
+    # built from the Philox words exactly like numpy's random_sample
+    w = torch.empty(4 * 16, dtype=torch.int32, device=dev)
+    nat.call("pst_philox_words", 5, 1, 0, 16, nat.ptr(w), nat.stream_ptr(dev))
+    w = w.cpu().numpy().view(np.uint32).reshape(16, 4).astype(np.uint64)
+    assert np.array_equal(uh[:16], ((w[:, 0] >> 5) * 67108864.0 + (w[:, 1] >> 6)) / 9007199254740992.0)
+    z = torch.empty(n, dtype=torch.float64, device=dev)
+    nat.call("pst_normal_f64", 5, 2, 0, n, 3.0, 2.0, None, None, nat.ptr(z), nat.stream_ptr(dev))
+    zh = (z.cpu().numpy() - 3.0) / 2.0
+    import scipy.stats
+    assert scipy.stats.kstest(zh, "norm").pvalue > 1e-4
+    assert abs(zh.mean()) < 5 / np.sqrt(n) and abs(zh.var() - 1) < 0.02
+
+
+# ------------------------------------------------------------------ lineage, draws in
+@pytest.mark.parametrize("name", ["abc", "bp2", "fork"])
+def test_walks_carry_relmeans_from_reference_draws(name):
+    branches, time, top, d = golden_lineage(name)
+    K, G = int(d["K"]), int(d["G"])
+    dev = torch.device(DEV)
+    t = ptree.Tree(topology=top, time=time, num_branches=len(branches), branch_points=1, modules=K, G=G)
+    tb = TreeTables(t, dev)
+    draws = ([d["u0_%s" % b] for b in branches], [d["v0_%s" % b] for b in branches],
+             [d["eta_%s" % b] for b in branches], [d["eps_%s" % b] for b in branches])
+    draws = (np.concatenate(draws[0]), np.concatenate(draws[1]), np.concatenate(draws[2]), draws[3])
+    W = sim._walk_programs([time[b] for b in branches], K, 0, None, None, dev, draws=draws)
+    raw = W.cpu().numpy()
+    for i, b in enumerate(branches):
+        lo = tb.row_base[i]
+        assert np.allclose(raw[lo:lo + time[b]], d["raw_%s" % b], rtol=1e-11, atol=1e-13)
+    # parent carry over the whole tree in breadth-first order
+    bfs = [b.item() if hasattr(b, "item") else b for b in sut.breadth_first_branches(t)]
+    parent = {}
+    for p, c in top:
+        parent.setdefault(c, p)
+    o_base = [int(tb.row_base[tb.index[b]]) for b in bfs]
+    o_T = [time[b] for b in bfs]
+    o_pl = [int(tb.row_base[tb.index[parent[b]]] + time[parent[b]] - 1) if b in parent else -1 for b in bfs]
+    nat.call("pst_walk_carry", len(bfs), K, _dev(o_base, torch.int32), _dev(o_T, torch.int32),
+             _dev(o_pl, torch.int32), nat.ptr(W), nat.stream_ptr(dev))
+    Wh = W.cpu().numpy()
+    for i, b in enumerate(branches):
+        lo = tb.row_base[i]
+        assert np.allclose(Wh[lo:lo + time[b]], d["W_%s" % b], rtol=1e-11, atol=1e-12)
+    # rel = W.H, M = exp(rel)*scale (fp64 and fp32), per-gene max
+    H = _dev(d["H"], torch.float64)
+    gs = _dev(d["gene_scale"], torch.float64)
+    rel = torch.empty((tb.P, G), dtype=torch.float64, device=dev)
+    m64 = torch.empty_like(rel)
+    m32 = torch.empty((tb.P, G), dtype=torch.float32, device=dev)
+    cmax = torch.full((G,), float("-inf"), dtype=torch.float64, device=dev)
+    nat.call("pst_rel_means", nat.ptr(W), nat.ptr(H), nat.ptr(gs), 0, tb.P, K, G, nat.ptr(rel), nat.ptr(m64),
+             nat.ptr(m32), nat.ptr(cmax), nat.stream_ptr(dev))
+    relh, m64h, m32h = rel.cpu().numpy(), m64.cpu().numpy(), m32.cpu().numpy()
+    for i, b in enumerate(branches):
+        lo = tb.row_base[i]
+        sl = slice(lo, lo + time[b])
+        assert np.allclose(relh[sl], d["rel_%s" % b], rtol=1e-11, atol=1e-12)
+        assert np.allclose(m64h[sl], d["M_%s" % b], rtol=1e-10, atol=0)
+        assert np.allclose(m32h[sl], d["M_%s" % b], rtol=2e-7, atol=0)
+    assert np.allclose(np.exp(cmax.cpu().numpy()), d["max_rel_exp"], rtol=1e-10)
+    # the host API form (calc_relat_means) gives the same
+    rm = sut.calc_relat_means(t, {b: d["W_%s" % b] for b in branches}, d["H"], device=dev)
+    for b in branches:
+        assert np.allclose(rm[b], d["rel_%s" % b], rtol=1e-11, atol=1e-12)
+
+
+def test_walk_scan_long_branch_matches_sequential():
+    # T > 32 exercises the chunk carry of the warp scan; K=3, two branches (T=1 edge case)
+    rng = np.random.RandomState(3)
+    Ts, K = [1000, 1, 33, 2], 3
+    u0 = rng.uniform(0.1, 1.5, size=len(Ts) * K)
+    v0 = rng.normal(0, 0.2, size=len(Ts) * K)
+    eta = rng.uniform(size=len(Ts) * K)
+    eps = [rng.normal(0, 2 / T, size=(K, T - 1)) for T in Ts]
+    W = sim._walk_programs(Ts, K, 0, None, None, torch.device(DEV), draws=(u0, v0, eta, eps)).cpu().numpy()
+    lo = 0
+    for j, T in enumerate(Ts):
+        want = orc.branch_programs_from_draws(u0[j * K:(j + 1) * K], v0[j * K:(j + 1) * K],
+                                              eta[j * K:(j + 1) * K], eps[j])
+        assert np.allclose(W[lo:lo + T], want, rtol=1e-10, atol=1e-11)
+        lo += T
+
+
+def test_walk_draw_distributions():
+    dev = torch.device(DEV)
+    T, K = 4001, 16
+    W = sim._walk_programs([T], K, 99, [0], [0], dev).cpu().numpy()
+    W2 = sim._walk_programs([T], K, 99, [0], [0], dev).cpu().numpy()
+    W3 = sim._walk_programs([T], K, 99, [0], [1], dev).cpu().numpy()
+    assert np.array_equal(W, W2) and not np.array_equal(W, W3)     # keyed by (seed, branch, attempt)
+    assert np.all(W[0] <= np.log(1.5))
+    # second differences: v[t+1]-eta v[t] = eps ~ N(0, 2/T); check its scale through var of accel
+    v = np.diff(W, axis=0)
+    assert np.all(np.isfinite(v))
+    # regress v[t+1] on v[t] -> eta in (0,1), residual std ~ 2/T
+    for k in range(K):
+        eta = np.dot(v[1:, k], v[:-1, k]) / np.dot(v[:-1, k], v[:-1, k])
+        res = v[1:, k] - eta * v[:-1, k]
+        assert -0.1 < eta < 1.1
+        assert abs(res.std() / (2 / T) - 1) < 0.1
+
+
+def test_pearson_count_matches_oracle():
+    rng = np.random.RandomState(0)
+    a, b = rng.normal(size=(20, 300)), rng.normal(size=(35, 300))
+    a[:, 5] = 1.0                                              # constant column -> NaN r -> not < 0
+    dev = torch.device(DEV)
+    got = sut._pearson_negative_count(_dev(a, torch.float64), _dev(b, torch.float64), dev)
+    assert got == orc.pearson_anticorrelated(a, b)
+    r = sut.pearson_between_programs(300, a, b, device=dev)
+    import scipy.stats
+    for g in (0, 17, 299):
+        assert abs(r[g] - scipy.stats.pearsonr(a[:20, g], b[:20, g])[0]) < 1e-12
+
+
+def test_simulate_lineage_properties():
+    np.random.seed(4)
+    top = ptree.Tree.gen_random_topology(3)
+    top = [[int(a), int(b)] for a, b in top]
+    time = {b: 25 + 3 * b for b in range(7)}
+    t = ptree.Tree(topology=top, time=time, num_branches=7, branch_points=3, modules=9, G=600)
+    rel, W, H = sim.simulate_lineage(t, a=0.05, seed=123, device=DEV)
+    assert H.shape == (9, 600) and list(rel.index) == list(sut.breadth_first_branches(t))
+    ot = orc.OTree(top, time)
+    for b in t.branches:
+        assert rel[b].shape == (time[b], 600) and W[b].shape == (time[b], 9)
+        assert np.allclose(rel[b], np.dot(W[b], H), rtol=1e-10, atol=1e-12)
+        assert rel[b].max() <= 8                                     # simulation.py:270
+        p = orc.parent_of(ot, b)
+        if p is not None:
+            assert np.allclose(W[b][0], W[p][-1], rtol=0, atol=1e-13)
+    for sib in t.get_parallel_branches().values():                   # every sibling pair diverges
+        for i in range(len(sib)):
+            for j in range(i + 1, len(sib)):
+                assert orc.pearson_anticorrelated(rel[sib[i]], rel[sib[j]]) > 0
+    rel2, W2, H2 = (None, None, None)
+    np.random.seed(4)
+    ptree.Tree.gen_random_topology(3)
+    rel2, W2, H2 = sim.simulate_lineage(t, a=0.05, seed=123, device=DEV)
+    assert np.array_equal(H, H2) and all(np.array_equal(rel[b], rel2[b]) for b in t.branches)
+    with pytest.warns(UserWarning):
+        sim.simulate_lineage(t, seed=1, device=DEV)
+
+
+# ------------------------------------------------------------------ index maps, draws in
+def _golden_tree(name):
+    branches, time, top, d = golden_lineage(name)
+    s = load_npz("sampling_%s.npz" % name)
+    dens, o = {}, 0
+    for b in branches:
+        dens[b] = s["density"][o:o + time[b]]
+        o += time[b]
+    t = ptree.Tree(topology=top, time=time, num_branches=len(branches), branch_points=1,
+                   modules=int(d["K"]), G=int(d["G"]), density=dens)
+    t.add_genes({b: d["M_%s" % b] for b in branches})
+    return t, s, d
+
+
+@pytest.mark.parametrize("name", ["abc", "bp2", "fork"])
+def test_index_maps_bit_exact_from_reference_draws(name):
+    t, s, d = _golden_tree(name)
+    # sample_density: uniforms of np.random.choice -> (pt, branch)
+    X, pt, br, sc = sim.sample_density(t, int(s["dens_N"]), alpha=s["alpha"], beta=s["beta"],
+                                       seed=1, device=DEV, uniforms=s["dens_u"])
+    assert np.array_equal(pt, s["dens_pt"]) and pt.dtype == np.int64
+    assert [str(b) for b in br] == [str(b) for b in s["dens_br"]]
+    # time series: normals -> times, uniforms -> branches
+    times = np.concatenate([
+        sim.draw_times(0, int(n), t.get_max_time(), device=DEV, normals=z)
+        for n, z in zip(s["ser_cells"], np.split(s["ser_zt"], np.cumsum(s["ser_cells"])[:-1]))])
+    assert np.array_equal(times, s["ser_pt"])
+    picked = sut.pick_branches(t, times, device=DEV, uniforms=s["ser_upick"])
+    assert [str(b) for b in picked] == [str(b) for b in s["ser_br"]]
+    # whole tree: deterministic
+    X, pt, br, sc = sim.sample_whole_tree(t, int(s["wt_n"]), alpha=s["alpha"], beta=s["beta"], seed=1, device=DEV)
+    assert np.array_equal(pt, s["wt_pt"]) and [str(b) for b in br] == [str(b) for b in s["wt_br"]]
+    assert X.shape == s["wt_X"].shape and X.dtype == np.int64
+    # scalings = exp(normals)
+    dev = torch.device(DEV)
+    s64 = torch.empty(len(s["dens_z"]), dtype=torch.float64, device=dev)
+    s32 = torch.empty(len(s["dens_z"]), dtype=torch.float32, device=dev)
+    nat.call("pst_scalings", _dev(s["dens_z"], torch.float64), len(s["dens_z"]), nat.ptr(s64),
+             nat.ptr(s32), nat.stream_ptr(dev))
+    assert np.allclose(s64.cpu().numpy(), s["dens_scalings"], rtol=1e-14)
+    assert np.allclose(s32.cpu().numpy(), s["dens_scalings"], rtol=1e-7)
+
+
+def test_pick_branch_many_candidates_numpy_sum_order():
+    # 12-way multifurcation: > 8 candidates exercises numpy's pairwise summation order
+    kids = list(range(1, 13))
+    top = [[0, k] for k in kids]
+    time = {0: 3}
+    time.update({k: 5 + k for k in kids})
+    rng = np.random.RandomState(8)
+    dens = {b: rng.uniform(0.1, 1, size=time[b]) for b in time}
+    tot = sum(v.sum() for v in dens.values())
+    dens = {b: v / tot for b, v in dens.items()}
+    t = ptree.Tree(topology=top, time=time, num_branches=13, branch_points=1, modules=2, G=4, density=dens)
+    ot = orc.OTree(top, time, density=dens)
+    pts = rng.randint(0, t.get_max_time(), size=3000)
+    u = rng.random_sample(3000)
+    got = sut.pick_branches(t, pts, device=DEV, uniforms=u)
+    want = orc.pick_branches_from_uniforms(ot, pts, u)
+    assert list(got) == want
+
+
+def test_nb_params_match_reference():
+    d = load_npz("nbparams.npz")
+    p, r = cm.get_pr_umi(d["a"], d["b"], d["m"], device=DEV)
+    assert np.allclose(p, d["p"], rtol=1e-12, atol=0) and np.allclose(r, d["r"], rtol=1e-12, atol=0)
+    p, r = cm.get_pr_umi(d["a2"], d["b2"], d["m"], device=DEV)
+    assert np.allclose(p, d["p2"], rtol=1e-9, atol=0) and np.allclose(r, d["r2"], rtol=1e-9, atol=0)
+    p, r = cm.get_pr_umi(0.1, 2.0, np.array([0.0, 1.0]), device=DEV)
+    assert p[0] == 0 and r[0] == 0
+
+
+# ------------------------------------------------------------------ counts
+def _flat_tree(mu, reps=1):
+    """A one-branch tree whose means rows are `mu` (len G) - every cell has the same mean."""
+    G = len(mu)
+    t = ptree.Tree(topology=[], time={0: reps}, num_branches=1, branch_points=0, modules=1, G=G)
+    t.add_genes({0: np.tile(np.asarray(mu, float), (reps, 1))})
+    return t
+
+
+REGIMES = [  # (mu, alpha, beta)   gamma shape r = mu/(alpha mu + beta - 1)
+    (1e-4, 0.2, 2.0), (0.05, 0.3, 1.5), (0.5, 0.2, 2.0), (1.8, 0.2, 2.0), (1.8, 0.02, 1.05),
+    (4.0, 1.0, 3.0), (9.0, 0.1, 2.0), (12.0, 0.05, 1.2), (30.0, 0.2, 2.0), (30.0, 0.001, 1.01),
+    (300.0, 0.3, 2.0), (3000.0, 0.1, 4.0), (2e4, 0.2, 2.0), (50.0, 0.0, 1 + 10e-9), (3.0, 0.0, 1 + 10e-9),
+    (0.7, 2.0, 1.2),
+]
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_counts_match_nb_distribution_per_regime(sampler):
+    import scipy.stats
+    mu = np.array([r[0] for r in REGIMES])
+    alpha = np.array([r[1] for r in REGIMES])
+    beta = np.array([r[2] for r in REGIMES])
+    N = 400000
+    t = _flat_tree(mu)
+    X = sim.draw_counts(t, np.zeros(N, int), [0] * N, np.ones(N), alpha, beta, seed=2024, device=DEV,
+                        dtype=np.int32, sampler=sampler)
+    theta = alpha * mu + beta - 1
+    r = mu / theta
+    p = 1 / (1 + theta)
+    rng = np.random.RandomState(1)
+    for g in range(len(mu)):
+        x = X[:, g]
+        var = alpha[g] * mu[g] ** 2 + beta[g] * mu[g]
+        # mean within 5 sigma, variance within 5 sigma (using the NB 4th central moment estimate)
+        assert abs(x.mean() - mu[g]) < 5 * np.sqrt(var / N), (g, x.mean(), mu[g])
+        ref = rng.negative_binomial(r[g], p[g], size=N)
+        m4 = np.mean((ref - ref.mean()) ** 4)
+        assert abs(x.var() - var) < 6 * np.sqrt(max(m4 - var ** 2, var ** 2) / N) + 1e-12, (g, x.var(), var)
+        # chi-square against the exact pmf over bins with expected count >= 20
+        hi = int(max(scipy.stats.nbinom.ppf(1 - 1e-4, r[g], p[g]), 4))
+        if hi < 5000:
+            pmf = scipy.stats.nbinom.pmf(np.arange(hi + 1), r[g], p[g])
+            obs = np.bincount(np.minimum(x, hi + 1), minlength=hi + 2).astype(float)
+            exp = np.append(pmf, max(1 - pmf.sum(), 0)) * N
+            # merge sparse bins
+            keep = exp >= 20
+            o = np.append(obs[keep], obs[~keep].sum())
+            e = np.append(exp[keep], exp[~keep].sum())
+            if e[-1] < 1e-9:
+                o, e = o[:-1], e[:-1]
+            chi2 = ((o - e) ** 2 / e).sum()
+            pval = scipy.stats.chi2.sf(chi2, len(e) - 1)
+            assert pval > 1e-6, (g, REGIMES[g], chi2, len(e), pval)
+        # two-sample KS against numpy's legacy generator on the same (n, p)
+        assert scipy.stats.ks_2samp(x, ref).pvalue > 1e-6, (g, REGIMES[g])
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_counts_match_reference_sampler_statistics(sampler):
+    """Same tree, alpha, beta as a reference run (golden fixture): per-gene totals of the CUDA
+    counts agree with the model mean/variance, as do the reference's own counts."""
+    t, s, d = _golden_tree("bp2")
+    N = 60000
+    X, pt, br, sc = sim.sample_density(t, N, alpha=s["alpha"], beta=s["beta"], seed=77, device=DEV, sampler=sampler)
+    ot = orc.OTree(t.topology, dict(t.time), G=t.G)
+    ot.means = t.means
+    mu = orc.cell_means(ot, pt, list(br), sc)
+    var = s["alpha"] * mu ** 2 + s["beta"] * mu
+    z = (X.sum(axis=0) - mu.sum(axis=0)) / np.sqrt(var.sum(axis=0))
+    assert abs(z.mean()) < 4 / np.sqrt(t.G) + 0.1 and 0.6 < z.std() < 1.4, (z.mean(), z.std())
+    zc = (X.sum(axis=1) - mu.sum(axis=1)) / np.sqrt(var.sum(axis=1))
+    assert abs(zc.mean()) < 0.05 and 0.9 < zc.std() < 1.1, (zc.mean(), zc.std())
+    # zero fraction vs P(0) = (1+theta)^(-r)
+    theta = s["alpha"] * mu + s["beta"] - 1
+    p0 = np.exp(-mu / theta * np.log1p(theta))
+    assert abs((X == 0).mean() - p0.mean()) < 5 * np.sqrt(p0.mean() * (1 - p0.mean()) / X.size) + 1e-4
+    # scalings are lognormal(0, 0.7) and keyed by the seed
+    assert abs(np.log(sc).mean()) < 0.02 and abs(np.log(sc).std() - 0.7) < 0.02
+    # density sampling follows tree.density
+    tb = TreeTables(t, torch.device(DEV))
+    dens = tb.density_packed(t)
+    rows = np.array([tb.row_base[tb.index[b if not hasattr(b, "item") else b.item()]] for b in br]) + pt - \
+        np.array([tb.branch_start[tb.index[b if not hasattr(b, "item") else b.item()]] for b in br])
+    obs = np.bincount(rows, minlength=tb.P)
+    import scipy.stats
+    assert scipy.stats.chisquare(obs, dens * N).pvalue > 1e-6
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_counts_bit_exact_across_partitions(sampler):
+    t, s, d = _golden_tree("fork")
+    N = 5003
+    kw = dict(alpha=s["alpha"], beta=s["beta"], seed=31337, device=DEV, dtype=np.int32, sampler=sampler)
+    full = sim.sample_density(t, N, **kw)
+    for world in (2, 3, 4, 8):
+        parts = [sim.sample_density(t, N, shard=(r, world), **kw) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+        assert list(np.concatenate([p[2] for p in parts])) == list(full[2])
+        assert np.array_equal(np.concatenate([p[3] for p in parts]), full[3])
+    full = sim.sample_whole_tree(t, 7, **kw)
+    parts = [sim.sample_whole_tree(t, 7, shard=(r, 4), **kw) for r in range(4)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+    full = sim.sample_pseudotime_series(t, [300, 200, 100], [0, 5, 12], [2.0, 3.0, 4.0], **kw)
+    parts = [sim.sample_pseudotime_series(t, [300, 200, 100], [0, 5, 12], [2.0, 3.0, 4.0], shard=(r, 2), **kw)
+             for r in range(2)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+    # different seed -> different counts; same seed -> same
+    again = sim.sample_density(t, N, **kw)
+    assert np.array_equal(again[0], sim.sample_density(t, N, **kw)[0])
+    kw["seed"] = 31338
+    assert not np.array_equal(again[0], sim.sample_density(t, N, **kw)[0])
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_streamed_host_output_and_launch_shape_invariance(sampler):
+    t, s, d = _golden_tree("bp2")
+    dev = torch.device(DEV)
+    tb = TreeTables(t, dev)
+    eng = CountEngine(t, tb, s["alpha"], s["beta"], dev, sampler=sampler)
+    n = 3000
+    rng = np.random.RandomState(2)
+    rows = _dev(rng.randint(0, tb.P, size=n), torch.int32)
+    sc = _dev(np.exp(rng.normal(0, 0.7, size=n)), torch.float32)
+    direct = eng.draw(rows, sc, 5, 1000).cpu()
+    host = torch.empty((n, t.G), dtype=torch.int32).pin_memory()
+    eng.draw_to_host(rows, sc, 5, 1000, host, chunk_cells=701)
+    assert torch.equal(direct, host)
+    eng.check()
+    # G not a multiple of 4 takes the scalar path: common genes agree bit for bit
+    G2 = t.G - 3
+    t2 = ptree.Tree(topology=t.topology, time=dict(t.time), num_branches=t.num_branches, branch_points=1,
+                    modules=t.modules, G=G2)
+    t2.add_genes({b: np.ascontiguousarray(t.means[b][:, :G2]) for b in t.branches})
+    eng2 = CountEngine(t2, TreeTables(t2, dev), s["alpha"][:G2], s["beta"][:G2], dev, sampler=sampler)
+    part = eng2.draw(rows, sc, 5, 1000).cpu()
+    assert torch.equal(part, direct[:, :G2])
+
+
+def test_domain_and_range_errors():
+    t = _flat_tree([1.0, 2.0, 0.0, 3.0])
+    with pytest.raises(ValueError):                     # mu == 0
+        sim.draw_counts(t, [0], [0], [1.0], 0.2, 2.0, seed=1, device=DEV)
+    t = _flat_tree([1.0, 2.0, 1.0, 3.0])
+    with pytest.raises(ValueError):                     # beta < 1 - alpha*mu
+        sim.draw_counts(t, [0], [0], [1.0], 0.0, 0.5, seed=1, device=DEV)
+    with pytest.raises(IndexError):                     # pseudotime outside the branch
+        sim.draw_counts(t, [5], [0], [1.0], 0.2, 2.0, seed=1, device=DEV)
+    with pytest.raises(KeyError):
+        sim.draw_counts(t, [0], [9], [1.0], 0.2, 2.0, seed=1, device=DEV)
+    X = sim.draw_counts(t, [], [], [], 0.2, 2.0, seed=1, device=DEV)          # empty input
+    assert X.shape == (0, 4)
+    t.means = None
+    with pytest.raises(ValueError):
+        sim.draw_counts(t, [0], [0], [1.0], 0.2, 2.0, seed=1, device=DEV)
+
+
+def test_reference_script_flow_and_restricted_sampler():
+    """The body of examples/generate_simN.py:86-113 and the minimal example
+    (simulation.py:289-316) run unchanged against this package."""
+    import prosstt_b200
+    prosstt_b200.install_as_prosstt()
+    from prosstt import simulation as psim, sim_utils as psut, tree as pt_mod  # noqa: F401
+    np.random.seed(17)
+    G = np.random.randint(100, 1001)
+    alpha = np.exp(np.random.normal(loc=np.log(0.2), scale=np.log(1.5), size=G))
+    beta = np.exp(np.random.normal(loc=np.log(1), scale=np.log(1.5), size=G)) + 1
+    top = pt_mod.Tree.gen_random_topology(2)
+    branches = np.unique(np.array(top).flatten())
+    time = {b: 50 for b in branches}
+    t = pt_mod.Tree(topology=top, time=time, num_branches=5, G=G)
+    uMs, Ws, H = psim.simulate_lineage(t, a=0.05, intra_branch_tol=0)
+    gene_scale = psut.simulate_base_gene_exp(t, uMs)
+    t.add_genes({b: np.exp(uMs[b]) * gene_scale for b in t.branches})
+    X, pseudotime, brns, scalings = psim.sample_density(t, t.get_max_time(), alpha=alpha, beta=beta)
+    assert X.shape == (t.get_max_time(), G) and X.dtype == np.int64 and X.flags["C_CONTIGUOUS"]
+    assert pseudotime.dtype == np.int64 and scalings.dtype == np.float64 and len(brns) == X.shape[0]
+    np.random.seed(92)
+    t = pt_mod.Tree()
+    X, pseudotime, brns, scalings = psim.sample_whole_tree_restricted(t)
+    assert X.shape == (80, 500) and set(brns) <= {"A", "B", "C"}
+    assert list(pseudotime) == list(range(80))
+    fused = psim.add_non_diff_genes(X, 10, {"base_expr": np.full(10, 3.0), "alpha": np.full(10, 0.2),
+                                            "beta": np.full(10, 2.0)}, scalings)
+    assert fused.shape == (80, 510) and np.array_equal(fused[:, :500], X)

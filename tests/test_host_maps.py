@@ -1,0 +1,185 @@
+"""Host layer (prosstt_b200.tree / sim_utils / device.TreeTables) against the fixtures
+produced by running the reference: integer maps are bit-exact.  CPU only."""
+import re
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_lineage, load_maps, load_npz, pairs_to_dict
+from prosstt_b200 import _native as nat
+from prosstt_b200 import sim_utils as sut, simulation as sim, tree as ptree, tree_utils as tu
+from prosstt_b200.device import TreeTables, choice_cdf
+
+MAPS = load_maps()
+
+
+def _tree(rec, **kw):
+    time = pairs_to_dict(rec["time"])
+    return ptree.Tree(topology=rec["topology"], time=time, num_branches=len(time),
+                      branch_points=rec["branch_points"], modules=3, G=7, **kw)
+
+
+@pytest.mark.parametrize("rec", MAPS, ids=[r["name"] for r in MAPS])
+def test_tree_maps_match_reference(rec):
+    t = _tree(rec)
+    assert t.branches == rec["branches"] and t.root == rec["root"]
+    bt = t.branch_times()
+    assert [[k, list(v)] for k, v in bt.items()] == rec["branch_times"]
+    zones = t.populate_timezone()
+    assert zones == rec["timezone"]
+    live = sut.assign_branches(bt, zones)
+    assert [[k, v] for k, v in live.items()] == rec["assignments"]
+    pt, br = sim.cover_whole_tree(t)
+    assert pt == rec["cover_pt"] and br == rec["cover_br"]
+    assert t.get_max_time() == rec["max_time"]
+    assert [str(b) for b in sut.breadth_first_branches(t)] == [str(b) for b in rec["bfs"]]
+    assert t.paths(t.root) == rec["paths"]
+    par = t.get_parallel_branches()
+    assert [[k if not hasattr(k, "item") else k.item(), list(v.tolist())] for k, v in par.items()] == rec["parallel"]
+    assert abs(sum(np.sum(v) for v in t.density.values()) - rec["density_sum"]) < 1e-15
+
+
+@pytest.mark.parametrize("rec", MAPS, ids=[r["name"] for r in MAPS])
+def test_device_tables_flatten_the_same_maps(rec):
+    t = _tree(rec)
+    tb = TreeTables(t, "cpu")
+    bt = t.branch_times()
+    assert tb.P == sum(t.time.values)
+    for i, b in enumerate(tb.names):
+        assert tb.branch_start[i] == bt[b][0] and tb.T[i] == t.time[b]
+    # packed positions are sample_density's concatenation (simulation.py:454-461)
+    want_pt = np.concatenate([np.arange(bt[b][0], bt[b][1] + 1) for b in t.branches])
+    assert np.array_equal(tb.pos_pt, want_pt)
+    assert [tb.names[c] for c in tb.pos_branch] == [b for b in t.branches for _ in range(t.time[b])]
+    # cover tables == cover_whole_tree
+    assert tb.cover_pt.tolist() == rec["cover_pt"]
+    assert [tb.names[c] for c in tb.cover_branch] == rec["cover_br"]
+    for e in range(len(tb.cover_pt)):
+        b = tb.cover_branch[e]
+        assert tb.cover_row[e] == tb.row_base[b] + tb.cover_pt[e] - tb.branch_start[b]
+    # candidates per zone == assign_branches
+    live = sut.assign_branches(bt, t.populate_timezone())
+    for z in range(len(tb.zone_lo)):
+        got = [tb.names[c] for c in tb.cand_branch[tb.cand_off[z]:tb.cand_off[z + 1]]]
+        assert got == live[z]
+    assert tb.max_time == rec["max_time"]
+
+
+def test_random_topology_matches_reference_stream():
+    # gen_random_topology consumes np.random.choice exactly like tree.py:82-113
+    for rec in MAPS:
+        m = re.match(r"random_s(\d+)_bp(\d+)", rec["name"])
+        if not m:
+            continue
+        np.random.seed(int(m.group(1)))
+        top = ptree.Tree.gen_random_topology(int(m.group(2)))
+        assert [[int(a), int(b)] for a, b in top] == rec["topology"]
+
+
+def test_tree_defaults_and_errors():
+    np.random.seed(0)
+    t = ptree.Tree()
+    assert t.branches == ["A", "B", "C"] and t.G == 500 and 6 <= t.modules <= 24
+    assert dict(t.branch_times()) == {"A": [0, 39], "B": [40, 79], "C": [40, 79]}
+    with pytest.raises(ValueError):
+        t.add_genes({"A": np.zeros((40, 500))})
+    with pytest.raises(ValueError):
+        t.add_genes({"A": np.zeros((40, 500)), "B": np.zeros((40, 500)), "C": np.zeros((39, 500))})
+    with pytest.raises(ValueError):
+        t.set_density({"A": np.ones(40)})
+    with pytest.raises(ValueError):
+        t.set_density({"A": np.ones(40), "B": np.ones(40), "C": np.ones(3)})
+    with pytest.raises(ValueError):
+        t.set_velocity({"A": np.ones(40)})
+    bad = ptree.Tree(topology=[[1, 2], [0, 1]], time={0: 3, 1: 3, 2: 3}, modules=1, G=1)
+    with pytest.raises(ValueError):
+        bad.branch_times()
+    t2 = ptree.Tree(modules=4)
+    t2.num_branches = 5
+    with pytest.raises(ValueError):          # simulation.py:254-256, raised before any GPU work
+        sim.simulate_lineage(t2, a=0.05)
+
+
+def test_newick():
+    t = ptree.Tree.from_newick("(A:50,B:50)C:50;", genes=10, modules=2)
+    assert t.branches == ["C", "A", "B"] and t.root == "C"
+    assert t.topology == [["C", "A"], ["C", "B"]] and t.num_branches == 3 and t.branch_points == 1
+    assert dict(t.time) == {"C": 50, "A": 50, "B": 50}
+    t = ptree.Tree.from_newick("((D,E)B:7,C:3)A;", genes=10, modules=2)
+    assert t.branches == ["A", "B", "D", "E", "C"]
+    assert dict(t.time) == {"A": 40, "B": 7, "D": 40, "E": 40, "C": 3}
+    assert t.topology == [["A", "B"], ["A", "C"], ["B", "D"], ["B", "E"]]
+    with pytest.raises(ValueError):
+        tu.newick_loads("((A,B)C;")
+
+
+def test_velocity_to_density():
+    t = ptree.Tree(modules=2)
+    vel = {b: np.linspace(1.0, 2.0, 40) for b in t.branches}
+    t.set_velocity(vel)
+    assert abs(sum(np.sum(v) for v in t.density.values()) - 1) < 1e-12
+    assert t.density["A"][0] > t.density["A"][-1]          # slow cells pile up
+
+
+def test_choice_cdf_validation():
+    cdf = choice_cdf(np.full(8, 0.125))
+    assert cdf[-1] == 1.0
+    with pytest.raises(ValueError):
+        choice_cdf([0.5, 0.6])
+    with pytest.raises(ValueError):
+        choice_cdf([1.5, -0.5])
+
+
+def test_timeseries_input_and_groups():
+    pts, cells, std = sut.process_timeseries_input([0, 10, 20], 100, 6.0)
+    assert cells.tolist() == [33, 33, 33] and std.tolist() == [2.0, 2.0, 2.0]
+    np.random.seed(1)
+    groups = sut.create_groups(4, 30)
+    assert len(groups) == 4 and sorted(g for grp in groups for g in grp) == sorted(list(range(30)) * 2)
+    assert sut.flat_order(4).tolist() == [[0, 0, 1], [1, 0, 2], [2, 0, 3], [3, 1, 2], [4, 1, 3], [5, 2, 3]]
+
+
+def test_host_side_draws_follow_the_reference_stream():
+    """generate_negbin_params / simulate_coefficients / simulate_base_gene_exp stay on the
+    global legacy numpy stream: same seed -> the reference's values."""
+    from prosstt_b200 import count_model as cm
+    d = load_npz("nbparams.npz")
+    np.random.seed(5)
+    a, b = cm.generate_negbin_params(type("T", (), {"G": 64})(), mean_alpha=0.2, mean_beta=2)
+    assert np.array_equal(a, d["gen_alpha"]) and np.array_equal(b, d["gen_beta"])
+    branches, time, top, L = golden_lineage("abc")
+    np.random.seed(int(L["seed"]))
+    t = ptree.Tree(topology=top, time=time, num_branches=3, branch_points=1, modules=int(L["K"]), G=int(L["G"]))
+    H = sim.simulate_coefficients(t, a=float(L["a"]))
+    assert np.array_equal(H, L["H"])                         # first draws after the seed
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = nat.load()
+    header = open(os.path.join(ROOT, "include", "prosstt_b200.h")).read()
+    declared = set(re.findall(r"\b(pst_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(nat.declared_symbols())
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.pst_abi_version() == 1
+    assert lib.pst_launch_count() == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    t = ptree.Tree(modules=2, G=8)
+    with pytest.raises(nat.NativeError):
+        sim.simulate_lineage(t, a=0.05)
+    with pytest.raises(nat.NativeError):
+        sim.sample_density(t, 10)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "prosstt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f

@@ -174,3 +174,15 @@ def test_philox_known_answers():
     for ctr, key, out in kat:
         got = orc.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
         assert tuple(int(x) for x in got) == out
+
+
+@pytest.mark.parametrize("name", ["abc", "bp2", "fork"])
+def test_oracle_simulate_lineage_replays_reference(name):
+    """Whole simulate_lineage (incl. its rejection loop) on the legacy stream."""
+    branches, time, top, d = golden_lineage(name)
+    t = orc.OTree(top, time, G=int(d["G"]), modules=int(d["K"]))
+    rel, W, H = orc.simulate_lineage(t, np.random.RandomState(int(d["seed"])), a=float(d["a"]),
+                                     rel_exp_cutoff=float(d["cutoff"]))
+    assert np.array_equal(H, d["H"])
+    for b in branches:
+        assert np.array_equal(W[b], d["W_%s" % b]) and np.array_equal(rel[b], d["rel_%s" % b])
