@@ -24,7 +24,8 @@ constexpr int kNumSM = 148;          // B200: 2 dies x 74 SMs
 // stream tags (third Philox counter word): one independent stream per use
 enum : uint32_t {
   TAG_WALK_U0 = 0x100, TAG_WALK_V0 = 0x101, TAG_WALK_ETA = 0x102, TAG_WALK_EPS = 0x103,
-  TAG_COUNT = 0x200,   // + draw index in the 4th counter word
+  TAG_COUNT = 0x200,   // per-(cell,gene) stream of the gamma-Poisson path, block# in word 4
+  TAG_QUAD = 0x201,    // one block per (cell, gene quad): the four inversion uniforms
 };
 
 // ---------------------------------------------------------------------------
@@ -54,6 +55,22 @@ __device__ __forceinline__ uint4 philox(const PhiloxKey &key, uint32_t c0, uint3
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Same function with the key schedule formed inline from the two seed words: when they are
+// kernel parameters the ten bumps live in the uniform datapath (no per-thread key registers,
+// no local memory).
+__device__ __forceinline__ uint4 philox_s(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                          uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)i * 0x9E3779B9u);
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)i * 0xBB67AE85u);
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 // 32 random bits -> float strictly inside (0,1): (w+0.5)*2^-32, top clamped to 1-2^-24
 __device__ __forceinline__ float u01(uint32_t w) {
   return fminf(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
@@ -68,6 +85,11 @@ __device__ __forceinline__ double normal_f64(uint4 r) {
   const double u2 = u53(r.z, r.w);
   return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
+
+// fast reciprocal / base-2 log / exp (one MUFU each, no slow-path branches)
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
   unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);

@@ -5,30 +5,36 @@
 //   mu    = means[row_of_cell[n]][g] * scaling[n]
 //   theta = alpha[g]*mu + (beta[g]-1)          gamma scale   (scipy p = 1/(1+theta))
 //   r     = mu / theta                         gamma shape   (scipy n)
-//   X     ~ Poisson( theta * Gamma(r) )
+//   X     ~ NB(r, 1/(1+theta))  ==  Poisson( theta * Gamma(r) )
 //
 // Work item = (cell, gene quad): one thread draws 4 neighbouring genes of one cell and
-// writes them with one 128-bit store; a warp writes 512 contiguous bytes of X.  Items are
-// a flat range so the grid is load-balanced for any G.  Every draw uses its own Philox
-// stream with counter (gene, cell_lo, TAG|cell_hi, block#), so counts do not depend on
-// the launch shape, the cell partition or the GPU count.
+// writes them with one 128-bit store; a warp writes 512 contiguous bytes of X.  Items are a
+// flat range so the grid is load-balanced for any G.  Every uniform is a pure function of
+// (seed, cell, gene or gene quad, draw index) through Philox4x32-10, so counts do not depend
+// on launch shape, cell partition or GPU count.
+//
+// Two samplers (both exact up to fp32 rounding, see DESIGN.md "sampler accuracy"):
+//   PST_SAMPLER_GAMMA_POISSON  the mixture exactly as numpy draws it: Marsaglia-Tsang gamma,
+//                              then Poisson by PTRS (lam >= 10) or inversion (lam < 10)
+//   PST_SAMPLER_HYBRID         direct inversion of the NB cdf with ONE uniform for small
+//                              means (branch-free unrolled head + compacted tail), the
+//                              mixture above for large means, both queue-compacted per warp
 #include "pst_common.cuh"
 
 namespace pst {
 
 // ---------------------------------------------------------------------------
-// per-(cell,gene) word stream
+// per-(cell,gene) word stream for the mixture path
 // ---------------------------------------------------------------------------
 struct GeneStream {
-  const PhiloxKey &key;
-  uint32_t c0, c1, c2, blk;
+  uint32_t k0, k1, c0, c1, c2, blk;
   uint4 buf;
   int left;
-  __device__ GeneStream(const PhiloxKey &k, uint32_t gene, int64_t cell)
-      : key(k), c0(gene), c1((uint32_t)cell),
+  __device__ GeneStream(uint32_t key0, uint32_t key1, uint32_t gene, int64_t cell)
+      : k0(key0), k1(key1), c0(gene), c1((uint32_t)cell),
         c2((TAG_COUNT << 16) | (uint32_t)((uint64_t)cell >> 32)), blk(0), left(0) {}
   __device__ __forceinline__ uint32_t next() {
-    if (left == 0) { buf = philox(key, c0, c1, c2, blk++); left = 4; }
+    if (left == 0) { buf = philox_s(k0, k1, c0, c1, c2, blk++); left = 4; }
     const uint32_t w = buf.x;
     buf.x = buf.y; buf.y = buf.z; buf.z = buf.w;
     --left;
@@ -37,21 +43,16 @@ struct GeneStream {
   __device__ __forceinline__ float uniform() { return u01(next()); }
 };
 
-// log(k!) : exact table below 16, Stirling series above (abs error < 1e-7 relative to 1)
-__device__ __forceinline__ float log_factorial_small(int k) {
-  const float tab[16] = {0.f, 0.f, 0.6931471806f, 1.7917594692f, 3.1780538303f, 4.7874917428f,
-                         6.5792512120f, 8.5251613611f, 10.6046029027f, 12.8018274801f,
-                         15.1044125730f, 17.5023078459f, 19.9872144957f, 22.5521638531f,
-                         25.1912211827f, 27.8992713838f};
-  return tab[k];
-}
+__constant__ float c_logfact[16] = {0.f, 0.f, 0.6931471806f, 1.7917594692f, 3.1780538303f,
+                                    4.7874917428f, 6.5792512120f, 8.5251613611f, 10.6046029027f,
+                                    12.8018274801f, 15.1044125730f, 17.5023078459f, 19.9872144957f,
+                                    22.5521638531f, 25.1912211827f, 27.8992713838f};
 
 // Poisson(lam), lam >= 10: PTRS transformed rejection (Hoermann 1993), the algorithm numpy's
 // legacy generator uses for lam >= 10.  The acceptance bound -lam + k log(lam) - log(k!) is
 // evaluated as k(log1p(y)-y) - log(sqrt(2 pi k)) - 1/(12k)+..., y = (lam-k)/k, which stays
 // accurate in fp32 for lam up to 2^24.
-template <class Stream>
-__device__ __forceinline__ float poisson_ptrs(float lam, Stream &rng) {
+__device__ __forceinline__ float poisson_ptrs(float lam, GeneStream &rng) {
   const float slam = sqrtf(lam);
   const float loglam = __logf(lam);
   const float b = 0.931f + 2.53f * slam;
@@ -68,7 +69,7 @@ __device__ __forceinline__ float poisson_ptrs(float lam, Stream &rng) {
     if (k < 0.f || (us < 0.013f && V > us)) continue;
     float bound;
     if (k < 16.f) {
-      bound = -lam + k * loglam - log_factorial_small((int)k);
+      bound = -lam + k * loglam - c_logfact[(int)k];
     } else {
       const float y = (lam - k) / k;
       const float ik = 1.0f / k;
@@ -81,8 +82,7 @@ __device__ __forceinline__ float poisson_ptrs(float lam, Stream &rng) {
 }
 
 // Poisson(lam), lam < 10: sequential inversion with one uniform
-template <class Stream>
-__device__ __forceinline__ float poisson_small(float lam, Stream &rng) {
+__device__ __forceinline__ float poisson_small(float lam, GeneStream &rng) {
   const float u = rng.uniform();
   float p = __expf(-lam), cdf = p, k = 0.f;
   while (u > cdf && k < 96.f) {
@@ -93,9 +93,8 @@ __device__ __forceinline__ float poisson_small(float lam, Stream &rng) {
   return k;
 }
 
-// standard gamma(shape a >= 2/3.. any a>=1 in use) / by Marsaglia-Tsang; returns d*v
-template <class Stream>
-__device__ __forceinline__ float gamma_mt(float a, Stream &rng) {
+// standard gamma, shape a >= 1, by Marsaglia-Tsang (2000); returns d*v
+__device__ __forceinline__ float gamma_mt(float a, GeneStream &rng) {
   const float d = a - 0.3333333333f;
   const float c = rsqrtf(9.0f * d);
   float v = 1.0f;
@@ -124,15 +123,8 @@ __device__ __forceinline__ float gamma_mt(float a, Stream &rng) {
   return d * v;
 }
 
-// one NB count by the gamma-Poisson mixture
-template <class Stream>
-__device__ __forceinline__ int nb_gamma_poisson(float mu, float alpha, float bm1, Stream &rng,
-                                                uint32_t &flag) {
-  const float theta = fmaf(alpha, mu, bm1);
-  if (!(mu > 0.f) || !(theta > 0.f) || !(mu < 3.0e38f) || !(theta < 3.0e38f)) {
-    flag |= PST_FLAG_DOMAIN;
-    return 0;
-  }
+// gamma-Poisson draw for valid (mu, theta): lambda = theta * Gamma(mu/theta), X ~ Poisson(lambda)
+__device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, GeneStream &rng, uint32_t &flag) {
   const float r = mu / theta;
   float g;
   if (r >= 1.0f) {
@@ -155,18 +147,22 @@ __device__ __forceinline__ int nb_gamma_poisson(float mu, float alpha, float bm1
   return (int)k;
 }
 
+__device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
+  return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
+}
+
 // ---------------------------------------------------------------------------
-// kernel v0: straight gamma-Poisson per count
+// kernel "gamma_poisson": the mixture for every count
 // ---------------------------------------------------------------------------
 constexpr int DC_THREADS = 256;
 
 template <bool VEC>
 __global__ void __launch_bounds__(DC_THREADS)
-draw_counts_gp_kernel(PhiloxKey key, const float *__restrict__ means, int64_t P, int64_t G, int64_t Q,
-                      const int32_t *__restrict__ row_of_cell, const float *__restrict__ scaling,
-                      const float *__restrict__ alpha, const float *__restrict__ beta_m1,
-                      int64_t cell0, int64_t n, int32_t *__restrict__ X, int64_t ldx,
-                      uint32_t *__restrict__ flags) {
+draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ means, int64_t P, int64_t G,
+                      int64_t Q, const int32_t *__restrict__ row_of_cell,
+                      const float *__restrict__ scaling, const float *__restrict__ alpha,
+                      const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
+                      int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags) {
   const int64_t items = n * Q;
   const int64_t stride = (int64_t)gridDim.x * DC_THREADS;
   uint32_t flag = 0;
@@ -199,8 +195,10 @@ draw_counts_gp_kernel(PhiloxKey key, const float *__restrict__ means, int64_t P,
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (VEC || g0 + j < G) {
-          GeneStream rng(key, (uint32_t)(g0 + j), cell0 + cell);
-          out[j] = nb_gamma_poisson(m[j] * s, a[j], b[j], rng, flag);
+          const float mu = m[j] * s, theta = fmaf(a[j], mu, b[j]);
+          if (!nb_domain_ok(mu, theta)) { flag |= PST_FLAG_DOMAIN; continue; }
+          GeneStream rng(key0, key1, (uint32_t)(g0 + j), cell0 + cell);
+          out[j] = nb_gamma_poisson_mt(mu, theta, rng, flag);
         }
       }
     }
@@ -215,6 +213,223 @@ draw_counts_gp_kernel(PhiloxKey key, const float *__restrict__ means, int64_t P,
   if (flag) atomicOr(flags, flag);
 }
 
+// ---------------------------------------------------------------------------
+// kernel "hybrid": distribution-identical, divergence-aware, warp-autonomous.
+//
+// Small means (mu <= HY_MU_MAX and variance mu(1+theta) <= HY_VAR_MAX): inversion of the NB
+//   cdf with one uniform u:  P(0) = (1+theta)^-r,  P(k+1) = P(k) (a + q k)/(k+1),
+//   q = theta/(1+theta), a = q r,  X = #{k : u > cdf(k)}.
+//   Head: KFIX terms fully unrolled and branch-free for the 4 genes of a thread.  The state is
+//   t_k = P(k) k! and d_k = cdf(k) - u, so one term costs FFMA (a+qk), FMUL (t), FFMA
+//   (d += t/k!, 1/k! an immediate) and one integer op adding the sign bit of d to the count.
+//   The four uniforms of a thread come from ONE Philox block keyed (cell, gene quad).
+//   Tail: counts still undecided after KFIX terms (u above the cdf) are pushed to a per-warp
+//   shared-memory queue and finished 32 at a time with k warp-uniform (1/(k+1) from a
+//   constant table), so the tail runs at full warp width whatever the mix of means.
+// Large means are pushed to a second per-warp queue and drawn 32 at a time by the mixture
+//   (Marsaglia-Tsang + PTRS) on their own per-(cell, gene) Philox stream.
+// The head writes the quad with one 128-bit store (0 in undecided slots); queue results are
+//   written with 4-byte stores after a __syncwarp (same warp, ordered).
+// The route depends on the parameters only, never on the uniforms, so the draw is unbiased.
+// ---------------------------------------------------------------------------
+constexpr int HY_WARPS = 4;                  // warps per CTA
+constexpr int HY_THREADS = HY_WARPS * 32;
+constexpr int HY_QCAP = 160;                 // 31 carried + 128 new entries, rounded up
+constexpr int HY_KMAX = 2048;
+constexpr float HY_MU_MAX = 16.0f, HY_VAR_MAX = 100.0f;
+__constant__ float c_inv[HY_KMAX + 2];
+static bool c_inv_ready = false;
+
+struct HyWarpQueues {
+  // inversion tail: p, d, a, q  + where the count goes
+  float sp[HY_QCAP], sd[HY_QCAP], sa[HY_QCAP], sq[HY_QCAP];
+  int s_cell[HY_QCAP], s_gene[HY_QCAP];
+  // mixture queue
+  float gm[HY_QCAP], gt[HY_QCAP];
+  int g_cell[HY_QCAP], g_gene[HY_QCAP];
+};
+
+// 1/k!, k = 0..16 (immediates after unrolling)
+#define PST_INV_FACT_TABLE {1.0f, 1.0f, 0.5f, 1.0f / 6, 1.0f / 24, 1.0f / 120, 1.0f / 720, 1.0f / 5040,        \
+                            1.0f / 40320, 1.0f / 362880, 1.0f / 3628800, 1.0f / 39916800, 1.0f / 479001600,     \
+                            1.0f / 6227020800.0f, 1.0f / 87178291200.0f, 1.0f / 1307674368000.0f,               \
+                            1.0f / 20922789888000.0f}
+
+template <int KFIX, bool VEC>
+__global__ void __launch_bounds__(HY_THREADS)
+draw_counts_hybrid_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ means, int64_t P,
+                          int64_t G, uint32_t Q, const int32_t *__restrict__ row_of_cell,
+                          const float *__restrict__ scaling, const float *__restrict__ alpha,
+                          const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
+                          int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags) {
+  __shared__ HyWarpQueues queues[HY_WARPS];
+  HyWarpQueues &wq = queues[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int64_t items = n * (int64_t)Q;
+  const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
+  const int64_t warp_id = (int64_t)blockIdx.x * HY_WARPS + (threadIdx.x >> 5);
+  // (cell, quad) of lane 0's item, advanced incrementally: no 64-bit division in the loop
+  const int64_t step_items = n_warps * 32;
+  const int64_t step_cells = step_items / Q;
+  const uint32_t step_quads = (uint32_t)(step_items - step_cells * Q);
+  int64_t base_cell = (warp_id * 32) / Q;
+  uint32_t base_quad = (uint32_t)(warp_id * 32 - base_cell * Q);
+  constexpr float inv_fact[17] = PST_INV_FACT_TABLE;
+  static_assert(KFIX >= 2 && KFIX <= 16, "KFIX out of range");
+  int ns = 0, ng = 0;                         // queue fill, warp-uniform
+  uint32_t flag = 0;
+
+  // finish 32 (or the last `cnt`) queued inversions at full width
+  auto drain_search = [&](int first, int cnt) {
+    const bool act = lane < cnt;
+    const int e = first + lane;
+    float pp = act ? wq.sp[e] : 0.f, dd = act ? wq.sd[e] : 1.f;
+    const float aa = act ? wq.sa[e] : 0.f, qq = act ? wq.sq[e] : 0.f;
+    int cn = KFIX;
+    for (int k = KFIX - 1; k < HY_KMAX; ++k) {
+      // undecided: u above the cdf (d < 0) and the cdf can still move
+      const bool open = (dd < 0.f) && (pp > 2.0e-8f);
+      if (!__any_sync(0xffffffffu, open)) break;
+      pp *= fmaf(qq, (float)k, aa) * c_inv[k + 1];
+      dd += pp;
+      cn += (open && dd < 0.f) ? 1 : 0;
+    }
+    if (act) X[(int64_t)wq.s_cell[e] * ldx + wq.s_gene[e]] = cn;
+  };
+  auto drain_mixture = [&](int first, int cnt) {
+    if (lane < cnt) {
+      const int e = first + lane;
+      GeneStream rng(key0, key1, (uint32_t)wq.g_gene[e], cell0 + wq.g_cell[e]);
+      X[(int64_t)wq.g_cell[e] * ldx + wq.g_gene[e]] = nb_gamma_poisson_mt(wq.gm[e], wq.gt[e], rng, flag);
+    }
+  };
+
+  for (int64_t base_item = warp_id * 32; base_item < items; base_item += step_items) {
+    // this lane's item
+    uint32_t quad = base_quad + (uint32_t)lane;
+    int64_t cell = base_cell;
+    while (quad >= Q) { quad -= Q; ++cell; }
+    const bool valid = base_item + lane < items;
+    int32_t row = -1;
+    if (valid) {
+      row = row_of_cell[cell];
+      if (row < 0 || row >= P) { flag |= PST_FLAG_ROW; row = -1; }
+    }
+    float t[4], d[4], a[4], q[4], mu[4], th[4];
+    int cnt[4], route[4];                  // route: 0 inversion, 1 mixture, 2 nothing to draw
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { t[j] = d[j] = a[j] = q[j] = mu[j] = th[j] = 0.f; cnt[j] = 0; route[j] = 2; }
+    const uint32_t g0 = quad * 4u;
+    if (row >= 0) {
+      const float s = scaling[cell];
+      float m[4], al[4], bm[4];
+      if (VEC) {
+        const float4 mv = __ldg(reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0));
+        const float4 av = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
+        m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+        al[0] = av.x; al[1] = av.y; al[2] = av.z; al[3] = av.w;
+        bm[0] = bv.x; bm[1] = bv.y; bm[2] = bv.z; bm[3] = bv.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = (int64_t)g0 + j < G;
+          m[j] = ok ? means[(int64_t)row * G + g0 + j] : 1.f;
+          al[j] = ok ? alpha[g0 + j] : 0.f;
+          bm[j] = ok ? beta_m1[g0 + j] : 1.f;
+        }
+      }
+      const int64_t gcell = cell0 + cell;
+      const uint4 rnd = philox_s(key0, key1, quad, (uint32_t)gcell,
+                                 (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
+      const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mu[j] = m[j] * s;
+        th[j] = fmaf(al[j], mu[j], bm[j]);
+        const bool masked = !VEC && ((int64_t)g0 + j >= G);
+        const bool ok = nb_domain_ok(mu[j], th[j]);
+        const float t1 = 1.0f + th[j];
+        const float ith = rcp_fast(th[j]);
+        q[j] = th[j] * rcp_fast(t1);
+        const float r = mu[j] * ith;
+        a[j] = q[j] * r;
+        // log2 P(0) = -r log2(1+theta); below theta = 0.1 use mu * (log1p(theta)/theta) by
+        // series so that the Poisson limit theta -> 0 is exact
+        float e2 = -r * lg2_fast(t1);
+        if (th[j] < 0.1f) {
+          const float x = th[j];
+          const float ser = fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 0.1428571429f, -0.1666666667f), 0.2f),
+                                                          -0.25f), 0.3333333333f), -0.5f), 1.0f);
+          e2 = -1.4426950409f * mu[j] * ser;
+        }
+        t[j] = ex2_fast(e2);                       // P(0)
+        d[j] = t[j] - u01(rw[j]);                  // cdf(0) - u
+        cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
+        const bool small = (mu[j] <= HY_MU_MAX) && (mu[j] * t1 <= HY_VAR_MAX);
+        route[j] = (!ok || masked) ? 2 : (small ? 0 : 1);
+        if (!ok && !masked) flag |= PST_FLAG_DOMAIN;
+      }
+      // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
+#pragma unroll
+      for (int k = 0; k < KFIX - 1; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          t[j] *= fmaf(q[j], (float)k, a[j]);                    // t_{k+1} = P(k+1) (k+1)!
+          d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
+          cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
+        }
+      }
+    }
+    // store the quad (undecided / mixture slots hold 0 until their queue is drained)
+    if (valid) {
+      int out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = (route[j] == 0 && !(d[j] < 0.f)) ? cnt[j] : 0;
+      if (VEC) {
+        __stcs(reinterpret_cast<int4 *>(X + cell * ldx + g0), make_int4(out[0], out[1], out[2], out[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((int64_t)g0 + j < G) X[cell * ldx + g0 + j] = out[j];
+      }
+    }
+    // enqueue (all lanes take part in the ballots)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool to_search = (route[j] == 0) && (d[j] < 0.f);
+      const bool to_mix = (route[j] == 1);
+      const unsigned ms = __ballot_sync(0xffffffffu, to_search);
+      const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
+      if (to_search) {
+        const int e = ns + __popc(ms & lt_mask);
+        wq.sp[e] = t[j] * inv_fact[KFIX - 1];                   // back to P(KFIX-1)
+        wq.sd[e] = d[j]; wq.sa[e] = a[j]; wq.sq[e] = q[j];
+        wq.s_cell[e] = (int)cell; wq.s_gene[e] = (int)(g0 + j);
+      }
+      if (to_mix) {
+        const int e = ng + __popc(mg & lt_mask);
+        wq.gm[e] = mu[j]; wq.gt[e] = th[j];
+        wq.g_cell[e] = (int)cell; wq.g_gene[e] = (int)(g0 + j);
+      }
+      ns += __popc(ms);
+      ng += __popc(mg);
+    }
+    __syncwarp();
+    while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
+    while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
+    __syncwarp();
+    // advance lane 0's (cell, quad)
+    base_cell += step_cells;
+    base_quad += step_quads;
+    if (base_quad >= Q) { base_quad -= Q; ++base_cell; }
+  }
+  if (ns > 0) drain_search(0, ns);
+  if (ng > 0) drain_mixture(0, ng);
+  if (flag) atomicOr(flags, flag);
+}
+
 }  // namespace pst
 
 using namespace pst;
@@ -226,7 +441,8 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const char *fn = "pst_draw_counts";
   PST_REQUIRE(P >= 0 && G >= 0 && n >= 0 && cell0 >= 0, fn, "negative size");
   PST_REQUIRE(ldx >= G, fn, "ldx < G");
-  PST_REQUIRE(G < (int64_t)1 << 32, fn, "G must be below 2^32");
+  PST_REQUIRE(G < (int64_t)1 << 31, fn, "G must be below 2^31");
+  PST_REQUIRE(n < (int64_t)1 << 31, fn, "at most 2^31-1 cells per call (shard or chunk the cells)");
   PST_REQUIRE(cell0 + n < (int64_t)1 << 48, fn, "cell index must be below 2^48");
   PST_REQUIRE(sampler == PST_SAMPLER_GAMMA_POISSON || sampler == PST_SAMPLER_HYBRID, fn, "unknown sampler");
   if (n == 0 || G == 0) return 0;
@@ -236,16 +452,36 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
                    ((uintptr_t)alpha % 16 == 0) && ((uintptr_t)beta_m1 % 16 == 0) &&
                    ((uintptr_t)X % 16 == 0);
   const int64_t items = n * Q;
-  int64_t blocks = (items + DC_THREADS - 1) / DC_THREADS;
-  const int64_t cap = (int64_t)kNumSM * 8 * 4;         // 4 waves of 8 CTAs per SM, then grid-stride
-  if (blocks > cap) blocks = cap;
-  const PhiloxKey key(seed);
+  const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
+  if (sampler == PST_SAMPLER_HYBRID) {
+    if (!c_inv_ready) {
+      static float h_inv[HY_KMAX + 2];
+      h_inv[0] = 0.f;
+      for (int i = 1; i < HY_KMAX + 2; ++i) h_inv[i] = 1.0f / (float)i;
+      const cudaError_t e = cudaMemcpyToSymbolAsync(c_inv, h_inv, sizeof(h_inv), 0, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "constant table upload failed"); }
+      c_inv_ready = true;
+    }
+    const int64_t need = (items + HY_THREADS - 1) / HY_THREADS;
+    const int64_t cap = (int64_t)kNumSM * 8;              // persistent CTAs: 8 x 4 warps per SM
+    const int64_t hb = need < cap ? need : cap;
+    if (vec)
+      draw_counts_hybrid_kernel<8, true><<<(unsigned)hb, HY_THREADS, 0, st>>>(
+          key0, key1, means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
+    else
+      draw_counts_hybrid_kernel<8, false><<<(unsigned)hb, HY_THREADS, 0, st>>>(
+          key0, key1, means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
+    return check_launch(fn);
+  }
+  int64_t blocks = (items + DC_THREADS - 1) / DC_THREADS;
+  const int64_t cap = (int64_t)kNumSM * 8 * 4;            // 4 waves of 8 CTAs per SM, then grid-stride
+  if (blocks > cap) blocks = cap;
   if (vec)
     draw_counts_gp_kernel<true><<<(unsigned)blocks, DC_THREADS, 0, st>>>(
-        key, means, P, G, Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
+        key0, key1, means, P, G, Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
   else
     draw_counts_gp_kernel<false><<<(unsigned)blocks, DC_THREADS, 0, st>>>(
-        key, means, P, G, Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
+        key0, key1, means, P, G, Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
   return check_launch(fn);
 }

@@ -23,7 +23,7 @@ from prosstt_b200 import count_model as cm, sim_utils as sut, simulation as sim,
 from prosstt_b200.device import CountEngine, TreeTables  # noqa: E402
 
 DEV = "cuda:0"
-SAMPLERS = ["gamma_poisson"]
+SAMPLERS = ["gamma_poisson", "hybrid"]
 
 
 def _dev(a, dtype):
