@@ -159,7 +159,10 @@ int pst_nb_params(const double *alpha, const double *beta, const double *mu,
  * Random numbers: Philox4x32-10 keyed by seed with counter (gene, global cell =
  * cell0+i, draw index) - independent of how cells are split over calls/GPUs.
  * beta_m1[g] = beta[g]-1 formed in fp64 by the caller.  X row stride is ldx
- * elements (>= G).  flags: one uint32, OR-ed with PST_FLAG_*. */
+ * elements (>= G).  flags: FOUR uint32 words, zeroed once by the caller: word 0 is OR-ed
+ * with PST_FLAG_*; words 1-2 are the hybrid sampler's work-scheduler scratch (used and
+ * reset to zero by every launch; launches sharing a status buffer must be stream-ordered);
+ * word 3 is reserved. */
 int pst_draw_counts(const float *means, int64_t P, int64_t G,
                     const int32_t *row_of_cell, const float *scaling,
                     const float *alpha, const float *beta_m1,

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libprosstt_b200.so")
+LIB_PATH = os.environ.get("PST_LIB", os.path.join(_PKG, "libprosstt_b200.so"))   # PST_LIB: developer override
 
 # flag bits (include/prosstt_b200.h)
 FLAG_DOMAIN, FLAG_ROW, FLAG_CLAMPED, FLAG_NOZONE = 1, 2, 4, 8

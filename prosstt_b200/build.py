@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PST_NVCC_DEFS", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -19,6 +19,7 @@
 //   PST_SAMPLER_HYBRID         direct inversion of the NB cdf with ONE uniform for small
 //                              means (branch-free unrolled head + compacted tail), the
 //                              mixture above for large means, both queue-compacted per warp
+#include <stdlib.h>
 #include "pst_common.cuh"
 
 namespace pst {
@@ -124,7 +125,8 @@ __device__ __forceinline__ float gamma_mt(float a, GeneStream &rng) {
 }
 
 // gamma-Poisson draw for valid (mu, theta): lambda = theta * Gamma(mu/theta), X ~ Poisson(lambda)
-__device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, GeneStream &rng, uint32_t &flag) {
+// (returns INT32_MAX when the count does not fit: the caller raises PST_FLAG_CLAMPED)
+__device__ __forceinline__ int nb_gamma_poisson_draw(float mu, float theta, GeneStream &rng) {
   const float r = mu / theta;
   float g;
   if (r >= 1.0f) {
@@ -143,8 +145,14 @@ __device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, GeneStrea
     const float u1 = rng.uniform(), u2 = rng.uniform();
     k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853072f * u2 - 3.1415926536f));
   }
-  if (k > 2147483520.f) { flag |= PST_FLAG_CLAMPED; return 2147483647; }
-  return (int)k;
+  return (k > 2147483520.f) ? 2147483647 : (int)k;
+}
+
+// out-of-line entry for the hybrid kernel's queue (keeps the head's register budget small)
+__device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, uint32_t key0, uint32_t key1,
+                                                uint32_t gene, int64_t cell) {
+  GeneStream rng(key0, key1, gene, cell);
+  return nb_gamma_poisson_draw(mu, theta, rng);
 }
 
 __device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
@@ -198,7 +206,8 @@ draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ me
           const float mu = m[j] * s, theta = fmaf(a[j], mu, b[j]);
           if (!nb_domain_ok(mu, theta)) { flag |= PST_FLAG_DOMAIN; continue; }
           GeneStream rng(key0, key1, (uint32_t)(g0 + j), cell0 + cell);
-          out[j] = nb_gamma_poisson_mt(mu, theta, rng, flag);
+          out[j] = nb_gamma_poisson_draw(mu, theta, rng);
+          if (out[j] == 2147483647) flag |= PST_FLAG_CLAMPED;
         }
       }
     }
@@ -216,7 +225,7 @@ draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ me
 // ---------------------------------------------------------------------------
 // kernel "hybrid": distribution-identical, divergence-aware, warp-autonomous.
 //
-// Small means (mu <= HY_MU_MAX and variance mu(1+theta) <= HY_VAR_MAX): inversion of the NB
+// Small means (mu <= HY_MU_MAX = 32 and variance mu(1+theta) <= HY_VAR_MAX = 400): inversion of the NB
 //   cdf with one uniform u:  P(0) = (1+theta)^-r,  P(k+1) = P(k) (a + q k)/(k+1),
 //   q = theta/(1+theta), a = q r,  X = #{k : u > cdf(k)}.
 //   Head: KFIX terms fully unrolled and branch-free for the 4 genes of a thread.  The state is
@@ -235,18 +244,14 @@ draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ me
 constexpr int HY_WARPS = 4;                  // warps per CTA
 constexpr int HY_THREADS = HY_WARPS * 32;
 constexpr int HY_QCAP = 160;                 // 31 carried + 128 new entries, rounded up
-constexpr int HY_KMAX = 2048;
-constexpr float HY_MU_MAX = 16.0f, HY_VAR_MAX = 100.0f;
-__constant__ float c_inv[HY_KMAX + 2];
-static bool c_inv_ready = false;
+constexpr int HY_KMAX = 2048;                // hard bound on inversion terms
+constexpr float HY_MU_MAX = 32.0f, HY_VAR_MAX = 400.0f;   // route: mean <= 32 and sd <= 20
+constexpr int HY_KFIX = 10;                                  // unrolled head terms
 
 struct HyWarpQueues {
-  // inversion tail: p, d, a, q  + where the count goes
-  float sp[HY_QCAP], sd[HY_QCAP], sa[HY_QCAP], sq[HY_QCAP];
-  int s_cell[HY_QCAP], s_gene[HY_QCAP];
-  // mixture queue
-  float gm[HY_QCAP], gt[HY_QCAP];
-  int g_cell[HY_QCAP], g_gene[HY_QCAP];
+  float4 se[HY_QCAP];       // inversion tail: P(k), cdf(k)-u, a, q
+  int2 sw[HY_QCAP];         //                 where the count goes: (cell, gene)
+  float4 ge[HY_QCAP];       // mixture: mu, theta, cell, gene (ints bit-cast)
 };
 
 // 1/k!, k = 0..16 (immediates after unrolling)
@@ -255,179 +260,247 @@ struct HyWarpQueues {
                             1.0f / 6227020800.0f, 1.0f / 87178291200.0f, 1.0f / 1307674368000.0f,               \
                             1.0f / 20922789888000.0f}
 
+#ifndef HY_MIN_CTAS
+#define HY_MIN_CTAS 8
+#endif
+constexpr int HY_CHUNK_ITERS = 64;           // warp-iterations per chunk (64*32 items = 8192 counts)
+
 template <int KFIX, bool VEC>
-__global__ void __launch_bounds__(HY_THREADS)
-draw_counts_hybrid_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ means, int64_t P,
+__global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
+draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, int64_t P,
                           int64_t G, uint32_t Q, const int32_t *__restrict__ row_of_cell,
                           const float *__restrict__ scaling, const float *__restrict__ alpha,
                           const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
-                          int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags) {
+                          int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags,
+                          float mu_max, float var_max) {
   __shared__ HyWarpQueues queues[HY_WARPS];
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int64_t items = n * (int64_t)Q;
+  const int64_t n_chunks = (items + HY_CHUNK_ITERS * 32 - 1) / (HY_CHUNK_ITERS * 32);
   const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
-  const int64_t warp_id = (int64_t)blockIdx.x * HY_WARPS + (threadIdx.x >> 5);
-  // (cell, quad) of lane 0's item, advanced incrementally: no 64-bit division in the loop
-  const int64_t step_items = n_warps * 32;
-  const int64_t step_cells = step_items / Q;
-  const uint32_t step_quads = (uint32_t)(step_items - step_cells * Q);
-  int64_t base_cell = (warp_id * 32) / Q;
-  uint32_t base_quad = (uint32_t)(warp_id * 32 - base_cell * Q);
+  const uint32_t key0 = key.k0[0], key1 = key.k1[0];
   constexpr float inv_fact[17] = PST_INV_FACT_TABLE;
   static_assert(KFIX >= 2 && KFIX <= 16, "KFIX out of range");
   int ns = 0, ng = 0;                         // queue fill, warp-uniform
   uint32_t flag = 0;
 
-  // finish 32 (or the last `cnt`) queued inversions at full width
+  // finish up to 32 queued inversions at full warp width; k is warp-uniform
   auto drain_search = [&](int first, int cnt) {
     const bool act = lane < cnt;
     const int e = first + lane;
-    float pp = act ? wq.sp[e] : 0.f, dd = act ? wq.sd[e] : 1.f;
-    const float aa = act ? wq.sa[e] : 0.f, qq = act ? wq.sq[e] : 0.f;
+    const float4 st = act ? wq.se[e] : make_float4(0.f, 1.f, 0.f, 0.f);
+    float pp = st.x, dd = st.y;
+    const float aa = st.z, qq = st.w;
     int cn = KFIX;
-    for (int k = KFIX - 1; k < HY_KMAX; ++k) {
-      // undecided: u above the cdf (d < 0) and the cdf can still move
-      const bool open = (dd < 0.f) && (pp > 2.0e-8f);
-      if (!__any_sync(0xffffffffu, open)) break;
-      pp *= fmaf(qq, (float)k, aa) * c_inv[k + 1];
-      dd += pp;
-      cn += (open && dd < 0.f) ? 1 : 0;
+    float kf = (float)(KFIX - 1);
+    for (int it = 0; it < HY_KMAX / 4; ++it) {
+      if (!__any_sync(0xffffffffu, dd < 0.f)) break;          // every cdf has passed its u
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const float k1 = kf + 1.0f;
+        pp *= fmaf(qq, kf, aa) * rcp_fast(k1);                 // P(k+1)
+        dd += pp;                                              // cdf(k+1) - u
+        cn += (int)(__float_as_uint(dd) >> 31);
+        kf = k1;
+      }
+      // u beyond what the fp32 cdf can reach (probability ~1e-7): stop counting
+      dd = (pp > 2.0e-8f) ? dd : 1.0f;
     }
-    if (act) X[(int64_t)wq.s_cell[e] * ldx + wq.s_gene[e]] = cn;
+    if (act) {
+      const int2 w = wq.sw[e];
+      X[(int64_t)w.x * ldx + w.y] = cn;
+    }
   };
   auto drain_mixture = [&](int first, int cnt) {
     if (lane < cnt) {
-      const int e = first + lane;
-      GeneStream rng(key0, key1, (uint32_t)wq.g_gene[e], cell0 + wq.g_cell[e]);
-      X[(int64_t)wq.g_cell[e] * ldx + wq.g_gene[e]] = nb_gamma_poisson_mt(wq.gm[e], wq.gt[e], rng, flag);
+      const float4 g = wq.ge[first + lane];
+      const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w);
+      int val = 0;
+      if (nb_domain_ok(g.x, g.y)) {
+        val = nb_gamma_poisson_mt(g.x, g.y, key0, key1, (uint32_t)gene, cell0 + ccell);
+        if (val == 2147483647) flag |= PST_FLAG_CLAMPED;
+      } else {
+        flag |= PST_FLAG_DOMAIN;
+      }
+      X[(int64_t)ccell * ldx + gene] = val;
     }
   };
 
-  for (int64_t base_item = warp_id * 32; base_item < items; base_item += step_items) {
-    // this lane's item
-    uint32_t quad = base_quad + (uint32_t)lane;
-    int64_t cell = base_cell;
-    while (quad >= Q) { quad -= Q; ++cell; }
-    const bool valid = base_item + lane < items;
-    int32_t row = -1;
-    if (valid) {
-      row = row_of_cell[cell];
-      if (row < 0 || row >= P) { flag |= PST_FLAG_ROW; row = -1; }
-    }
-    float t[4], d[4], a[4], q[4], mu[4], th[4];
-    int cnt[4], route[4];                  // route: 0 inversion, 1 mixture, 2 nothing to draw
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { t[j] = d[j] = a[j] = q[j] = mu[j] = th[j] = 0.f; cnt[j] = 0; route[j] = 2; }
+  struct Operands { float4 m, a, b; };
+  // loads of one item's operands; lanes past the end read item (row 0, quad 0)
+  auto fetch = [&](int32_t row, uint32_t quad, Operands &o) {
     const uint32_t g0 = quad * 4u;
-    if (row >= 0) {
-      const float s = scaling[cell];
+    if (VEC) {
+      o.m = __ldg(reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0));
+      o.a = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
+      o.b = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
+    } else {
       float m[4], al[4], bm[4];
-      if (VEC) {
-        const float4 mv = __ldg(reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0));
-        const float4 av = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
-        const float4 bv = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
-        m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-        al[0] = av.x; al[1] = av.y; al[2] = av.z; al[3] = av.w;
-        bm[0] = bv.x; bm[1] = bv.y; bm[2] = bv.z; bm[3] = bv.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool ok = (int64_t)g0 + j < G;
-          m[j] = ok ? means[(int64_t)row * G + g0 + j] : 1.f;
-          al[j] = ok ? alpha[g0 + j] : 0.f;
-          bm[j] = ok ? beta_m1[g0 + j] : 1.f;
-        }
-      }
-      const int64_t gcell = cell0 + cell;
-      const uint4 rnd = philox_s(key0, key1, quad, (uint32_t)gcell,
-                                 (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
-      const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        mu[j] = m[j] * s;
-        th[j] = fmaf(al[j], mu[j], bm[j]);
-        const bool masked = !VEC && ((int64_t)g0 + j >= G);
-        const bool ok = nb_domain_ok(mu[j], th[j]);
-        const float t1 = 1.0f + th[j];
-        const float ith = rcp_fast(th[j]);
-        q[j] = th[j] * rcp_fast(t1);
-        const float r = mu[j] * ith;
-        a[j] = q[j] * r;
-        // log2 P(0) = -r log2(1+theta); below theta = 0.1 use mu * (log1p(theta)/theta) by
-        // series so that the Poisson limit theta -> 0 is exact
-        float e2 = -r * lg2_fast(t1);
-        if (th[j] < 0.1f) {
-          const float x = th[j];
-          const float ser = fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 0.1428571429f, -0.1666666667f), 0.2f),
-                                                          -0.25f), 0.3333333333f), -0.5f), 1.0f);
-          e2 = -1.4426950409f * mu[j] * ser;
-        }
-        t[j] = ex2_fast(e2);                       // P(0)
-        d[j] = t[j] - u01(rw[j]);                  // cdf(0) - u
-        cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
-        const bool small = (mu[j] <= HY_MU_MAX) && (mu[j] * t1 <= HY_VAR_MAX);
-        route[j] = (!ok || masked) ? 2 : (small ? 0 : 1);
-        if (!ok && !masked) flag |= PST_FLAG_DOMAIN;
+        const bool ok = (int64_t)g0 + j < G;
+        m[j] = ok ? means[(int64_t)row * G + g0 + j] : 1.f;
+        al[j] = ok ? alpha[g0 + j] : 0.f;
+        bm[j] = ok ? beta_m1[g0 + j] : 1.f;
       }
-      // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
-#pragma unroll
-      for (int k = 0; k < KFIX - 1; ++k) {
+      o.m = make_float4(m[0], m[1], m[2], m[3]);
+      o.a = make_float4(al[0], al[1], al[2], al[3]);
+      o.b = make_float4(bm[0], bm[1], bm[2], bm[3]);
+    }
+  };
+  // per-cell scalars; a bad row index raises the flag and disables the cell
+  auto cell_info = [&](uint32_t cell, int32_t &row, float &s, bool &row_ok) {
+    row = row_of_cell[cell];
+    s = scaling[cell];
+    row_ok = (uint64_t)(uint32_t)row < (uint64_t)P && row >= 0;
+    if (!row_ok) { flag |= PST_FLAG_ROW; row = 0; }
+  };
+
+  // chunks are handed out dynamically (flags[1] is the next-chunk counter): warps whose
+  // queues drain more often simply take fewer chunks
+  for (;;) {
+    unsigned claimed = 0;
+    if (lane == 0) claimed = atomicAdd(&flags[1], 1u);
+    const int64_t chunk = (int64_t)__shfl_sync(0xffffffffu, claimed, 0);
+    const bool last = chunk >= n_chunks;      // no work left: flush the queues and leave
+    if (!last) {
+      const int64_t item0 = chunk * (HY_CHUNK_ITERS * 32);
+      const int64_t left = items - item0;
+      const int chunk_items = left < HY_CHUNK_ITERS * 32 ? (int)left : HY_CHUNK_ITERS * 32;
+      const int iters = (chunk_items + 31) >> 5;
+      // (cell, quad) of this lane's first item: one 64-bit division per chunk
+      uint32_t cell = (uint32_t)(item0 / Q);
+      uint32_t quad = (uint32_t)(item0 - (int64_t)cell * Q) + (uint32_t)lane;
+      while (quad >= Q) { quad -= Q; ++cell; }
+      if (lane >= chunk_items) { cell = 0; quad = 0; }
+      int32_t row; float s; bool row_ok;
+      cell_info(cell, row, s, row_ok);
+      Operands cur, nxt;
+      fetch(row, quad, cur);
+      for (int it = 0; it < iters; ++it) {
+        // ---- prefetch the next item's operands (same cell unless the row of X wraps)
+        uint32_t ncell = cell, nquad = quad + 32u;
+        int32_t nrow = row; float nsc = s; bool nrow_ok = row_ok;
+        const bool nvalid = (it + 1) * 32 + lane < chunk_items;
+        if (nquad >= Q) {
+          while (nquad >= Q) { nquad -= Q; ++ncell; }
+          if (!nvalid) { ncell = 0; nquad = 0; }
+          cell_info(ncell, nrow, nsc, nrow_ok);
+        }
+        if (!nvalid) { nquad = 0; if (ncell != 0) { ncell = 0; cell_info(0u, nrow, nsc, nrow_ok); } }
+        if (it + 1 < iters) fetch(nrow, nquad, nxt);
+
+        // ---- this item
+        const bool valid = it * 32 + lane < chunk_items;
+        const bool live = valid && row_ok;
+        const uint32_t g0 = quad * 4u;
+        const float m[4] = {cur.m.x, cur.m.y, cur.m.z, cur.m.w};
+        const float al[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
+        const float bm[4] = {cur.b.x, cur.b.y, cur.b.z, cur.b.w};
+        const int64_t gcell = cell0 + cell;
+        const uint4 rnd = philox(key, quad, (uint32_t)gcell,
+                                 (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
+        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
+        int cnt[4];
+        bool small[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          t[j] *= fmaf(q[j], (float)k, a[j]);                    // t_{k+1} = P(k+1) (k+1)!
-          d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
-          cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
+          mu[j] = m[j] * s;
+          th[j] = fmaf(al[j], mu[j], bm[j]);
+          const float t1 = 1.0f + th[j];
+          const float r = mu[j] * rcp_fast(th[j]);
+          q[j] = th[j] * rcp_fast(t1);
+          a[j] = q[j] * r;
+          e2[j] = -r * lg2_fast(t1);                 // log2 P(0) = -r log2(1+theta)
+          // inversion only for small mean and variance; comparisons are false on NaN
+          small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * t1 <= var_max);
         }
-      }
-    }
-    // store the quad (undecided / mixture slots hold 0 until their queue is drained)
-    if (valid) {
-      int out[4];
+        // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
+        if (fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < 0.1f) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = (route[j] == 0 && !(d[j] < 0.f)) ? cnt[j] : 0;
-      if (VEC) {
-        __stcs(reinterpret_cast<int4 *>(X + cell * ldx + g0), make_int4(out[0], out[1], out[2], out[3]));
-      } else {
+          for (int j = 0; j < 4; ++j) {
+            const float x = th[j];
+            const float ser = fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 0.1428571429f, -0.1666666667f), 0.2f),
+                                                            -0.25f), 0.3333333333f), -0.5f), 1.0f);
+            e2[j] = (x < 0.1f) ? -1.4426950409f * mu[j] * ser : e2[j];
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((int64_t)g0 + j < G) X[cell * ldx + g0 + j] = out[j];
-      }
-    }
-    // enqueue (all lanes take part in the ballots)
+        for (int j = 0; j < 4; ++j) {
+          t[j] = ex2_fast(e2[j]);                     // P(0)
+          d[j] = t[j] - u01(rw[j]);                   // cdf(0) - u
+          cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
+        }
+        // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool to_search = (route[j] == 0) && (d[j] < 0.f);
-      const bool to_mix = (route[j] == 1);
-      const unsigned ms = __ballot_sync(0xffffffffu, to_search);
-      const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
-      if (to_search) {
-        const int e = ns + __popc(ms & lt_mask);
-        wq.sp[e] = t[j] * inv_fact[KFIX - 1];                   // back to P(KFIX-1)
-        wq.sd[e] = d[j]; wq.sa[e] = a[j]; wq.sq[e] = q[j];
-        wq.s_cell[e] = (int)cell; wq.s_gene[e] = (int)(g0 + j);
+        for (int k = 0; k < KFIX - 1; ++k) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            t[j] *= fmaf(q[j], (float)k, a[j]);                    // t_{k+1} = P(k+1) (k+1)!
+            d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
+            cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
+          }
+        }
+        bool to_search[4], to_mix[4];
+        int out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in_range = live && (VEC || (int64_t)g0 + j < G);
+          to_search[j] = in_range && small[j] && (d[j] < 0.f);
+          to_mix[j] = in_range && !small[j];
+          out[j] = (small[j] && !(d[j] < 0.f)) ? cnt[j] : 0;
+        }
+        // store the quad (undecided / mixture slots hold 0 until their queue is drained)
+        if (valid) {
+          int32_t *dst = X + (int64_t)cell * ldx + g0;
+          if (VEC) {
+            __stcs(reinterpret_cast<int4 *>(dst), make_int4(out[0], out[1], out[2], out[3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if ((int64_t)g0 + j < G) dst[j] = out[j];
+          }
+        }
+        // enqueue (all lanes take part in the ballots)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned ms = __ballot_sync(0xffffffffu, to_search[j]);
+          const unsigned mg = __ballot_sync(0xffffffffu, to_mix[j]);
+          if (to_search[j]) {
+            const int e = ns + __popc(ms & lt_mask);
+            wq.se[e] = make_float4(t[j] * inv_fact[KFIX - 1], d[j], a[j], q[j]);   // back to P(KFIX-1)
+            wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
+          }
+          if (to_mix[j]) {
+            const int e = ng + __popc(mg & lt_mask);
+            wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
+          }
+          ns += __popc(ms);
+          ng += __popc(mg);
+        }
+        __syncwarp();
+        while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
+        while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
+        __syncwarp();
+        // rotate the pipeline
+        cell = ncell; quad = nquad; row = nrow; s = nsc; row_ok = nrow_ok;
+        cur = nxt;
       }
-      if (to_mix) {
-        const int e = ng + __popc(mg & lt_mask);
-        wq.gm[e] = mu[j]; wq.gt[e] = th[j];
-        wq.g_cell[e] = (int)cell; wq.g_gene[e] = (int)(g0 + j);
-      }
-      ns += __popc(ms);
-      ng += __popc(mg);
+    } else {
+      if (ns > 0) drain_search(0, ns);
+      if (ng > 0) drain_mixture(0, ng);
+      break;
     }
-    __syncwarp();
-    while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
-    while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
-    __syncwarp();
-    // advance lane 0's (cell, quad)
-    base_cell += step_cells;
-    base_quad += step_quads;
-    if (base_quad >= Q) { base_quad -= Q; ++base_cell; }
   }
-  if (ns > 0) drain_search(0, ns);
-  if (ng > 0) drain_mixture(0, ng);
   if (flag) atomicOr(flags, flag);
+  // the last warp to leave rearms the scheduler words for the next launch
+  if (lane == 0) {
+    const unsigned done = atomicAdd(&flags[2], 1u);
+    if (done == (unsigned)n_warps - 1u) { flags[1] = 0u; flags[2] = 0u; __threadfence(); }
+  }
 }
 
 }  // namespace pst
@@ -455,23 +528,34 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
   if (sampler == PST_SAMPLER_HYBRID) {
-    if (!c_inv_ready) {
-      static float h_inv[HY_KMAX + 2];
-      h_inv[0] = 0.f;
-      for (int i = 1; i < HY_KMAX + 2; ++i) h_inv[i] = 1.0f / (float)i;
-      const cudaError_t e = cudaMemcpyToSymbolAsync(c_inv, h_inv, sizeof(h_inv), 0, cudaMemcpyHostToDevice, st);
-      if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "constant table upload failed"); }
-      c_inv_ready = true;
+    // developer knobs (profiling only; they change the bit stream, never set them in production)
+    static const int kfix = getenv("PST_HY_KFIX") ? atoi(getenv("PST_HY_KFIX")) : HY_KFIX;
+    static const float mu_max = getenv("PST_HY_MU_MAX") ? (float)atof(getenv("PST_HY_MU_MAX")) : HY_MU_MAX;
+    static const float var_max = getenv("PST_HY_VAR_MAX") ? (float)atof(getenv("PST_HY_VAR_MAX")) : HY_VAR_MAX;
+    static const int ctas_per_sm = getenv("PST_HY_CTAS") ? atoi(getenv("PST_HY_CTAS")) : HY_MIN_CTAS;
+    const int64_t n_chunks = (items + HY_CHUNK_ITERS * 32 - 1) / (HY_CHUNK_ITERS * 32);
+    PST_REQUIRE(n_chunks < ((int64_t)1 << 31), fn, "too many work chunks in one call (chunk the cells)");
+    const int64_t need = (n_chunks + HY_WARPS - 1) / HY_WARPS;
+    const int64_t cap = (int64_t)kNumSM * ctas_per_sm;    // persistent CTAs of 4 warps, one wave
+    const unsigned hb = (unsigned)(need < cap ? need : cap);
+#define PST_LAUNCH_HYBRID(KF)                                                                              \
+    do {                                                                                                   \
+      if (vec) draw_counts_hybrid_kernel<KF, true><<<hb, HY_THREADS, 0, st>>>(                             \
+          PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
+          ldx, flags, mu_max, var_max);                                                                    \
+      else draw_counts_hybrid_kernel<KF, false><<<hb, HY_THREADS, 0, st>>>(                                \
+          PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
+          ldx, flags, mu_max, var_max);                                                                    \
+    } while (0)
+    switch (kfix) {
+      case 4: PST_LAUNCH_HYBRID(4); break;
+      case 6: PST_LAUNCH_HYBRID(6); break;
+      case 8: PST_LAUNCH_HYBRID(8); break;
+      case 12: PST_LAUNCH_HYBRID(12); break;
+      case 16: PST_LAUNCH_HYBRID(16); break;
+      default: PST_LAUNCH_HYBRID(HY_KFIX); break;
     }
-    const int64_t need = (items + HY_THREADS - 1) / HY_THREADS;
-    const int64_t cap = (int64_t)kNumSM * 8;              // persistent CTAs: 8 x 4 warps per SM
-    const int64_t hb = need < cap ? need : cap;
-    if (vec)
-      draw_counts_hybrid_kernel<8, true><<<(unsigned)hb, HY_THREADS, 0, st>>>(
-          key0, key1, means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
-    else
-      draw_counts_hybrid_kernel<8, false><<<(unsigned)hb, HY_THREADS, 0, st>>>(
-          key0, key1, means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
+#undef PST_LAUNCH_HYBRID
     return check_launch(fn);
   }
   int64_t blocks = (items + DC_THREADS - 1) / DC_THREADS;

@@ -178,7 +178,7 @@ class CountEngine(object):
         self.means = means_table(tree, tables, dev)
         self.alpha, self.beta_m1 = gene_params(alpha, beta, self.G, dev)
         self.sampler = nat.SAMPLERS[sampler]
-        self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # status + scheduler scratch
 
     def draw(self, rows, scaling32, seed, cell0, out=None):
         """Sample X for the cells described by rows/scaling32 (device tensors); global
@@ -219,7 +219,7 @@ class CountEngine(object):
 
     def check(self):
         """One device->host read of the status word; raises like the reference would."""
-        word = int(self.flags.item())
+        word = int(self.flags[0].item())
         if word:
-            self.flags.zero_()
+            self.flags[0].zero_()
             raise_flags(word)

@@ -26,7 +26,7 @@ from prosstt_b200 import count_model as cm
 from prosstt_b200 import sim_utils as sut
 from prosstt_b200.device import CountEngine, TreeTables, choice_cdf, raise_flags
 
-DEFAULT_SAMPLER = "gamma_poisson"
+DEFAULT_SAMPLER = "hybrid"
 
 
 # =============================================================================== lineage
