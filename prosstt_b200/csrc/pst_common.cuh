@@ -91,6 +91,24 @@ __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ft
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// L2 residency hints: the means table is re-read by every cell (keep), X is written once (stream)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float *ptr, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void stg_i4_hint(int32_t *ptr, int4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
   unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);
   unsigned long long old = *p;

@@ -260,6 +260,9 @@ struct HyWarpQueues {
                             1.0f / 6227020800.0f, 1.0f / 87178291200.0f, 1.0f / 1307674368000.0f,               \
                             1.0f / 20922789888000.0f}
 
+#ifndef HY_STORE_MODE
+#define HY_STORE_MODE 5   // bits 0-1: X store 0 = st.cs, 1 = default, 2 = L2 evict_first hint; bit 2: means evict_last
+#endif
 #ifndef HY_MIN_CTAS
 #define HY_MIN_CTAS 8
 #endif
@@ -285,6 +288,8 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   static_assert(KFIX >= 2 && KFIX <= 16, "KFIX out of range");
   int ns = 0, ng = 0;                         // queue fill, warp-uniform
   uint32_t flag = 0;
+  const uint64_t keep = l2_policy_evict_last(), stream_out = l2_policy_evict_first();
+  (void)keep; (void)stream_out;
 
   // finish up to 32 queued inversions at full warp width; k is warp-uniform
   auto drain_search = [&](int first, int cnt) {
@@ -333,7 +338,8 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   auto fetch = [&](int32_t row, uint32_t quad, Operands &o) {
     const uint32_t g0 = quad * 4u;
     if (VEC) {
-      o.m = __ldg(reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0));
+      o.m = (HY_STORE_MODE & 4) ? ldg_f4_hint(means + (int64_t)row * G + g0, keep)
+                                : __ldg(reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0));
       o.a = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
       o.b = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
     } else {
@@ -457,7 +463,10 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         if (valid) {
           int32_t *dst = X + (int64_t)cell * ldx + g0;
           if (VEC) {
-            __stcs(reinterpret_cast<int4 *>(dst), make_int4(out[0], out[1], out[2], out[3]));
+            const int4 v = make_int4(out[0], out[1], out[2], out[3]);
+            if ((HY_STORE_MODE & 3) == 0) __stcs(reinterpret_cast<int4 *>(dst), v);
+            else if ((HY_STORE_MODE & 3) == 1) *reinterpret_cast<int4 *>(dst) = v;
+            else stg_i4_hint(dst, v, stream_out);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
