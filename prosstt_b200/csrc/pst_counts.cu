@@ -260,13 +260,10 @@ struct HyWarpQueues {
                             1.0f / 6227020800.0f, 1.0f / 87178291200.0f, 1.0f / 1307674368000.0f,               \
                             1.0f / 20922789888000.0f}
 
-#ifndef HY_STORE_MODE
-#define HY_STORE_MODE 5   // bits 0-1: X store 0 = st.cs, 1 = default, 2 = L2 evict_first hint; bit 2: means evict_last
-#endif
 #ifndef HY_MIN_CTAS
 #define HY_MIN_CTAS 8
 #endif
-constexpr int HY_CHUNK_ITERS = 64;           // warp-iterations per chunk (64*32 items = 8192 counts)
+constexpr int HY_CHUNK_CELLS = 64;           // cells per chunk (x 32 quads = 8192 counts)
 
 template <int KFIX, bool VEC>
 __global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
@@ -280,16 +277,14 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int64_t items = n * (int64_t)Q;
-  const int64_t n_chunks = (items + HY_CHUNK_ITERS * 32 - 1) / (HY_CHUNK_ITERS * 32);
+  const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * (int64_t)((Q + 31u) / 32u);
   const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
   const uint32_t key0 = key.k0[0], key1 = key.k1[0];
   constexpr float inv_fact[17] = PST_INV_FACT_TABLE;
   static_assert(KFIX >= 2 && KFIX <= 16, "KFIX out of range");
   int ns = 0, ng = 0;                         // queue fill, warp-uniform
   uint32_t flag = 0;
-  const uint64_t keep = l2_policy_evict_last(), stream_out = l2_policy_evict_first();
-  (void)keep; (void)stream_out;
+  const uint64_t keep = l2_policy_evict_last();
 
   // finish up to 32 queued inversions at full warp width; k is warp-uniform
   auto drain_search = [&](int first, int cnt) {
@@ -333,35 +328,22 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     }
   };
 
-  struct Operands { float4 m, a, b; };
-  // loads of one item's operands; lanes past the end read item (row 0, quad 0)
-  auto fetch = [&](int32_t row, uint32_t quad, Operands &o) {
-    const uint32_t g0 = quad * 4u;
-    if (VEC) {
-      o.m = (HY_STORE_MODE & 4) ? ldg_f4_hint(means + (int64_t)row * G + g0, keep)
-                                : __ldg(reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0));
-      o.a = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
-      o.b = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
-    } else {
-      float m[4], al[4], bm[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = (int64_t)g0 + j < G;
-        m[j] = ok ? means[(int64_t)row * G + g0 + j] : 1.f;
-        al[j] = ok ? alpha[g0 + j] : 0.f;
-        bm[j] = ok ? beta_m1[g0 + j] : 1.f;
-      }
-      o.m = make_float4(m[0], m[1], m[2], m[3]);
-      o.a = make_float4(al[0], al[1], al[2], al[3]);
-      o.b = make_float4(bm[0], bm[1], bm[2], bm[3]);
-    }
-  };
-  // per-cell scalars; a bad row index raises the flag and disables the cell
-  auto cell_info = [&](uint32_t cell, int32_t &row, float &s, bool &row_ok) {
+  // Work decomposition: a chunk is a strip of 32 gene quads (one per lane, 128 genes = 512
+  // contiguous bytes of each X row) times HY_CHUNK_CELLS consecutive cells.  The per-gene
+  // parameters are loaded once per chunk; per cell only the means float4 (coalesced across
+  // the warp) and the two per-cell scalars are read, one and two cells ahead of their use.
+  const uint32_t n_strips = (Q + 31u) / 32u;
+  auto cell_scalars = [&](int64_t cell, int32_t &row, float &s) {
     row = row_of_cell[cell];
     s = scaling[cell];
-    row_ok = (uint64_t)(uint32_t)row < (uint64_t)P && row >= 0;
-    if (!row_ok) { flag |= PST_FLAG_ROW; row = 0; }
+  };
+  auto load_means = [&](int32_t row, uint32_t g0) -> float4 {
+    const int32_t r = ((uint32_t)row < (uint64_t)P) ? row : 0;       // bad rows are flagged at use
+    if (VEC) return ldg_f4_hint(means + (int64_t)r * G + g0, keep);
+    float m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = ((int64_t)g0 + j < G) ? means[(int64_t)r * G + g0 + j] : 1.f;
+    return make_float4(m[0], m[1], m[2], m[3]);
   };
 
   // chunks are handed out dynamically (flags[1] is the next-chunk counter): warps whose
@@ -369,141 +351,142 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   for (;;) {
     unsigned claimed = 0;
     if (lane == 0) claimed = atomicAdd(&flags[1], 1u);
-    const int64_t chunk = (int64_t)__shfl_sync(0xffffffffu, claimed, 0);
-    const bool last = chunk >= n_chunks;      // no work left: flush the queues and leave
-    if (!last) {
-      const int64_t item0 = chunk * (HY_CHUNK_ITERS * 32);
-      const int64_t left = items - item0;
-      const int chunk_items = left < HY_CHUNK_ITERS * 32 ? (int)left : HY_CHUNK_ITERS * 32;
-      const int iters = (chunk_items + 31) >> 5;
-      // (cell, quad) of this lane's first item: one 64-bit division per chunk
-      uint32_t cell = (uint32_t)(item0 / Q);
-      uint32_t quad = (uint32_t)(item0 - (int64_t)cell * Q) + (uint32_t)lane;
-      while (quad >= Q) { quad -= Q; ++cell; }
-      if (lane >= chunk_items) { cell = 0; quad = 0; }
-      int32_t row; float s; bool row_ok;
-      cell_info(cell, row, s, row_ok);
-      Operands cur, nxt;
-      fetch(row, quad, cur);
-      for (int it = 0; it < iters; ++it) {
-        // ---- prefetch the next item's operands (same cell unless the row of X wraps)
-        uint32_t ncell = cell, nquad = quad + 32u;
-        int32_t nrow = row; float nsc = s; bool nrow_ok = row_ok;
-        const bool nvalid = (it + 1) * 32 + lane < chunk_items;
-        if (nquad >= Q) {
-          while (nquad >= Q) { nquad -= Q; ++ncell; }
-          if (!nvalid) { ncell = 0; nquad = 0; }
-          cell_info(ncell, nrow, nsc, nrow_ok);
-        }
-        if (!nvalid) { nquad = 0; if (ncell != 0) { ncell = 0; cell_info(0u, nrow, nsc, nrow_ok); } }
-        if (it + 1 < iters) fetch(nrow, nquad, nxt);
-
-        // ---- this item
-        const bool valid = it * 32 + lane < chunk_items;
-        const bool live = valid && row_ok;
-        const uint32_t g0 = quad * 4u;
-        const float m[4] = {cur.m.x, cur.m.y, cur.m.z, cur.m.w};
-        const float al[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w};
-        const float bm[4] = {cur.b.x, cur.b.y, cur.b.z, cur.b.w};
-        const int64_t gcell = cell0 + cell;
-        const uint4 rnd = philox(key, quad, (uint32_t)gcell,
-                                 (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
-        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-        float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
-        int cnt[4];
-        bool small[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mu[j] = m[j] * s;
-          th[j] = fmaf(al[j], mu[j], bm[j]);
-          const float t1 = 1.0f + th[j];
-          const float r = mu[j] * rcp_fast(th[j]);
-          q[j] = th[j] * rcp_fast(t1);
-          a[j] = q[j] * r;
-          e2[j] = -r * lg2_fast(t1);                 // log2 P(0) = -r log2(1+theta)
-          // inversion only for small mean and variance; comparisons are false on NaN
-          small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * t1 <= var_max);
-        }
-        // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
-        if (fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < 0.1f) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = th[j];
-            const float ser = fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 0.1428571429f, -0.1666666667f), 0.2f),
-                                                            -0.25f), 0.3333333333f), -0.5f), 1.0f);
-            e2[j] = (x < 0.1f) ? -1.4426950409f * mu[j] * ser : e2[j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          t[j] = ex2_fast(e2[j]);                     // P(0)
-          d[j] = t[j] - u01(rw[j]);                   // cdf(0) - u
-          cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
-        }
-        // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
-#pragma unroll
-        for (int k = 0; k < KFIX - 1; ++k) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            t[j] *= fmaf(q[j], (float)k, a[j]);                    // t_{k+1} = P(k+1) (k+1)!
-            d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
-            cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
-          }
-        }
-        bool to_search[4], to_mix[4];
-        int out[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool in_range = live && (VEC || (int64_t)g0 + j < G);
-          to_search[j] = in_range && small[j] && (d[j] < 0.f);
-          to_mix[j] = in_range && !small[j];
-          out[j] = (small[j] && !(d[j] < 0.f)) ? cnt[j] : 0;
-        }
-        // store the quad (undecided / mixture slots hold 0 until their queue is drained)
-        if (valid) {
-          int32_t *dst = X + (int64_t)cell * ldx + g0;
-          if (VEC) {
-            const int4 v = make_int4(out[0], out[1], out[2], out[3]);
-            if ((HY_STORE_MODE & 3) == 0) __stcs(reinterpret_cast<int4 *>(dst), v);
-            else if ((HY_STORE_MODE & 3) == 1) *reinterpret_cast<int4 *>(dst) = v;
-            else stg_i4_hint(dst, v, stream_out);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if ((int64_t)g0 + j < G) dst[j] = out[j];
-          }
-        }
-        // enqueue (all lanes take part in the ballots)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned ms = __ballot_sync(0xffffffffu, to_search[j]);
-          const unsigned mg = __ballot_sync(0xffffffffu, to_mix[j]);
-          if (to_search[j]) {
-            const int e = ns + __popc(ms & lt_mask);
-            wq.se[e] = make_float4(t[j] * inv_fact[KFIX - 1], d[j], a[j], q[j]);   // back to P(KFIX-1)
-            wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
-          }
-          if (to_mix[j]) {
-            const int e = ng + __popc(mg & lt_mask);
-            wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
-          }
-          ns += __popc(ms);
-          ng += __popc(mg);
-        }
-        __syncwarp();
-        while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
-        while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
-        __syncwarp();
-        // rotate the pipeline
-        cell = ncell; quad = nquad; row = nrow; s = nsc; row_ok = nrow_ok;
-        cur = nxt;
-      }
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    if ((int64_t)claimed >= n_chunks) break;                  // no work left
+    const uint32_t cgroup = claimed / n_strips;
+    const uint32_t strip = claimed - cgroup * n_strips;
+    const uint32_t quad = strip * 32u + (uint32_t)lane;
+    const bool lane_ok = quad < Q;
+    const uint32_t g0 = (lane_ok ? quad : 0u) * 4u;
+    const int64_t cell_lo = (int64_t)cgroup * HY_CHUNK_CELLS;
+    const int n_cells = (int)((n - cell_lo) < HY_CHUNK_CELLS ? (n - cell_lo) : HY_CHUNK_CELLS);
+    // per-gene parameters of this lane's quad, once per chunk
+    float al[4], bm[4];
+    if (VEC) {
+      const float4 av = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
+      const float4 bv = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
+      al[0] = av.x; al[1] = av.y; al[2] = av.z; al[3] = av.w;
+      bm[0] = bv.x; bm[1] = bv.y; bm[2] = bv.z; bm[3] = bv.w;
     } else {
-      if (ns > 0) drain_search(0, ns);
-      if (ng > 0) drain_mixture(0, ng);
-      break;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (int64_t)g0 + j < G;
+        al[j] = ok ? alpha[g0 + j] : 0.f;
+        bm[j] = ok ? beta_m1[g0 + j] : 1.f;
+      }
+    }
+    // software pipeline: scalars two cells ahead, means one cell ahead
+    int32_t row, row1; float s, s1;
+    cell_scalars(cell_lo, row, s);
+    cell_scalars(cell_lo + (n_cells > 1 ? 1 : 0), row1, s1);
+    float4 mcur = load_means(row, g0);
+    for (int ci = 0; ci < n_cells; ++ci) {
+      const int64_t cell = cell_lo + ci;
+      int32_t row2; float s2;
+      cell_scalars(cell_lo + (ci + 2 < n_cells ? ci + 2 : n_cells - 1), row2, s2);
+      const float4 mnext = load_means(row1, g0);
+
+      // ---- this cell's quad
+      const bool row_ok = (uint32_t)row < (uint64_t)P;
+      if (!row_ok) flag |= PST_FLAG_ROW;
+      const bool live = lane_ok && row_ok;
+      const float m[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
+      const int64_t gcell = cell0 + cell;
+      const uint4 rnd = philox(key, quad, (uint32_t)gcell,
+                               (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
+      const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+      float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
+      int cnt[4];
+      bool small[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mu[j] = m[j] * s;
+        th[j] = fmaf(al[j], mu[j], bm[j]);
+        const float t1 = 1.0f + th[j];
+        const float r = mu[j] * rcp_fast(th[j]);
+        q[j] = th[j] * rcp_fast(t1);
+        a[j] = q[j] * r;
+        e2[j] = -r * lg2_fast(t1);                 // log2 P(0) = -r log2(1+theta)
+        // inversion only for small mean and variance; comparisons are false on NaN
+        small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * t1 <= var_max);
+      }
+      // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
+      if (fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < 0.1f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = th[j];
+          const float ser = fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 0.1428571429f, -0.1666666667f), 0.2f),
+                                                          -0.25f), 0.3333333333f), -0.5f), 1.0f);
+          e2[j] = (x < 0.1f) ? -1.4426950409f * mu[j] * ser : e2[j];
+        }
+      }
+      // large means: queue them for the mixture now, so mu/theta are dead during the head
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool to_mix = live && !small[j] && (VEC || (int64_t)g0 + j < G);
+        const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
+        if (to_mix) {
+          const int e = ng + __popc(mg & lt_mask);
+          wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
+        }
+        ng += __popc(mg);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[j] = ex2_fast(e2[j]);                     // P(0)
+        d[j] = t[j] - u01(rw[j]);                   // cdf(0) - u
+        cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
+      }
+      // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
+#pragma unroll
+      for (int k = 0; k < KFIX - 1; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          t[j] *= fmaf(q[j], (float)k, a[j]);                    // t_{k+1} = P(k+1) (k+1)!
+          d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
+          cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
+        }
+      }
+      bool to_search[4];
+      int out[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in_range = live && (VEC || (int64_t)g0 + j < G);
+        to_search[j] = in_range && small[j] && (d[j] < 0.f);
+        out[j] = (small[j] && !(d[j] < 0.f)) ? cnt[j] : 0;
+      }
+      // store the quad (undecided / mixture slots hold 0 until their queue is drained)
+      if (lane_ok) {
+        int32_t *dst = X + cell * ldx + g0;
+        if (VEC) {
+          *reinterpret_cast<int4 *>(dst) = make_int4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((int64_t)g0 + j < G) dst[j] = out[j];
+        }
+      }
+      // enqueue the undecided inversions (all lanes take part in the ballots)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned ms = __ballot_sync(0xffffffffu, to_search[j]);
+        if (to_search[j]) {
+          const int e = ns + __popc(ms & lt_mask);
+          wq.se[e] = make_float4(t[j] * inv_fact[KFIX - 1], d[j], a[j], q[j]);   // back to P(KFIX-1)
+          wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
+        }
+        ns += __popc(ms);
+      }
+      __syncwarp();
+      while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
+      while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
+      __syncwarp();
+      // rotate the pipeline
+      row = row1; s = s1; row1 = row2; s1 = s2; mcur = mnext;
     }
   }
+  if (ns > 0) drain_search(0, ns);
+  if (ng > 0) drain_mixture(0, ng);
   if (flag) atomicOr(flags, flag);
   // the last warp to leave rearms the scheduler words for the next launch
   if (lane == 0) {
@@ -542,7 +525,7 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
     static const float mu_max = getenv("PST_HY_MU_MAX") ? (float)atof(getenv("PST_HY_MU_MAX")) : HY_MU_MAX;
     static const float var_max = getenv("PST_HY_VAR_MAX") ? (float)atof(getenv("PST_HY_VAR_MAX")) : HY_VAR_MAX;
     static const int ctas_per_sm = getenv("PST_HY_CTAS") ? atoi(getenv("PST_HY_CTAS")) : HY_MIN_CTAS;
-    const int64_t n_chunks = (items + HY_CHUNK_ITERS * 32 - 1) / (HY_CHUNK_ITERS * 32);
+    const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * ((Q + 31) / 32);
     PST_REQUIRE(n_chunks < ((int64_t)1 << 31), fn, "too many work chunks in one call (chunk the cells)");
     const int64_t need = (n_chunks + HY_WARPS - 1) / HY_WARPS;
     const int64_t cap = (int64_t)kNumSM * ctas_per_sm;    // persistent CTAs of 4 warps, one wave
