@@ -162,13 +162,22 @@ int pst_nb_params(const double *alpha, const double *beta, const double *mu,
  * elements (>= G).  flags: FOUR uint32 words, zeroed once by the caller: word 0 is OR-ed
  * with PST_FLAG_*; words 1-2 are the hybrid sampler's work-scheduler scratch (used and
  * reset to zero by every launch; launches sharing a status buffer must be stream-ordered);
- * word 3 is reserved. */
+ * word 3 is reserved.
+ * cell_order (optional, may be NULL): a permutation of [0,n) giving the order in which the
+ * cells are visited (hybrid sampler only; see pst_group_cells_by_row). */
 int pst_draw_counts(const float *means, int64_t P, int64_t G,
                     const int32_t *row_of_cell, const float *scaling,
                     const float *alpha, const float *beta_m1,
                     uint64_t seed, int64_t cell0, int64_t n,
                     int32_t *X, int64_t ldx, uint32_t *flags, int32_t sampler,
-                    void *stream);
+                    const int32_t *cell_order, void *stream);
+
+/* Counting sort of the cells by tree row: order[] lists the cells of row 0, then row 1, ...
+ * (arbitrary order inside a row).  bins: P uint32 words of scratch.  Feeding `order` to
+ * pst_draw_counts makes concurrently running warps share means rows (L2/L1 hits instead of
+ * DRAM re-reads); it never changes the counts. */
+int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int32_t P,
+                           uint32_t *bins, int32_t *order, void *stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -20,6 +20,7 @@
 //                              means (branch-free unrolled head + compacted tail), the
 //                              mixture above for large means, both queue-compacted per warp
 #include <stdlib.h>
+#include <algorithm>
 #include "pst_common.cuh"
 
 namespace pst {
@@ -272,7 +273,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
                           const float *__restrict__ scaling, const float *__restrict__ alpha,
                           const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
                           int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags,
-                          float mu_max, float var_max) {
+                          const int32_t *__restrict__ cell_order, float mu_max, float var_max) {
   __shared__ HyWarpQueues queues[HY_WARPS];
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -333,7 +334,14 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   // parameters are loaded once per chunk; per cell only the means float4 (coalesced across
   // the warp) and the two per-cell scalars are read, one and two cells ahead of their use.
   const uint32_t n_strips = (Q + 31u) / 32u;
-  auto cell_scalars = [&](int64_t cell, int32_t &row, float &s) {
+  // cells are visited in `cell_order` (grouped by tree row so that concurrently running warps
+  // share means rows in L2/L1); results do not depend on the order
+#ifdef HY_NO_ORDER
+  auto cell_at = [&](int64_t pos) -> int32_t { return (int32_t)pos; };
+#else
+  auto cell_at = [&](int64_t pos) -> int32_t { return cell_order ? cell_order[pos] : (int32_t)pos; };
+#endif
+  auto cell_scalars = [&](int32_t cell, int32_t &row, float &s) {
     row = row_of_cell[cell];
     s = scaling[cell];
   };
@@ -375,15 +383,18 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         bm[j] = ok ? beta_m1[g0 + j] : 1.f;
       }
     }
-    // software pipeline: scalars two cells ahead, means one cell ahead
+    // software pipeline: cell id three cells ahead, its scalars two ahead, its means one ahead
+    const int64_t last_pos = cell_lo + n_cells - 1;
+    int32_t cell = cell_at(cell_lo), cell1 = cell_at(min(cell_lo + 1, last_pos));
+    int32_t cell2 = cell_at(min(cell_lo + 2, last_pos));
     int32_t row, row1; float s, s1;
-    cell_scalars(cell_lo, row, s);
-    cell_scalars(cell_lo + (n_cells > 1 ? 1 : 0), row1, s1);
+    cell_scalars(cell, row, s);
+    cell_scalars(cell1, row1, s1);
     float4 mcur = load_means(row, g0);
     for (int ci = 0; ci < n_cells; ++ci) {
-      const int64_t cell = cell_lo + ci;
+      const int32_t cell3 = cell_at(min(cell_lo + ci + 3, last_pos));
       int32_t row2; float s2;
-      cell_scalars(cell_lo + (ci + 2 < n_cells ? ci + 2 : n_cells - 1), row2, s2);
+      cell_scalars(cell2, row2, s2);
       const float4 mnext = load_means(row1, g0);
 
       // ---- this cell's quad
@@ -457,7 +468,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       }
       // store the quad (undecided / mixture slots hold 0 until their queue is drained)
       if (lane_ok) {
-        int32_t *dst = X + cell * ldx + g0;
+        int32_t *dst = X + (int64_t)cell * ldx + g0;
         if (VEC) {
           *reinterpret_cast<int4 *>(dst) = make_int4(out[0], out[1], out[2], out[3]);
         } else {
@@ -482,7 +493,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
       __syncwarp();
       // rotate the pipeline
-      row = row1; s = s1; row1 = row2; s1 = s2; mcur = mnext;
+      cell = cell1; row = row1; s = s1; cell1 = cell2; row1 = row2; s1 = s2; cell2 = cell3; mcur = mnext;
     }
   }
   if (ns > 0) drain_search(0, ns);
@@ -495,14 +506,74 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   }
 }
 
+// ---------------------------------------------------------------------------
+// cells grouped by tree row (counting sort): order[] lists the cells of row 0, then row 1, ...
+// ---------------------------------------------------------------------------
+__global__ void row_histogram_kernel(const int32_t *__restrict__ row_of_cell, int64_t n, int32_t P,
+                                     uint32_t *__restrict__ bins) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = row_of_cell[i];
+    atomicAdd(&bins[(uint32_t)r < (uint32_t)P ? r : 0], 1u);
+  }
+}
+
+__global__ void row_scan_kernel(uint32_t *bins, int32_t P) {      // exclusive scan, one CTA
+  __shared__ uint32_t part[1024];
+  const int t = threadIdx.x;
+  const int per = (P + 1023) / 1024;
+  const int lo = t * per, hi = min(P, lo + per);
+  uint32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += bins[i];
+  part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const uint32_t v = t >= off ? part[t - off] : 0u;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[t] - sum;
+  for (int i = lo; i < hi; ++i) { const uint32_t c = bins[i]; bins[i] = run; run += c; }
+}
+
+__global__ void row_scatter_kernel(const int32_t *__restrict__ row_of_cell, int64_t n, int32_t P,
+                                   uint32_t *__restrict__ bins, int32_t *__restrict__ order) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = row_of_cell[i];
+    order[atomicAdd(&bins[(uint32_t)r < (uint32_t)P ? r : 0], 1u)] = (int32_t)i;
+  }
+}
+
 }  // namespace pst
 
 using namespace pst;
 
+extern "C" int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int32_t P,
+                                      uint32_t *bins, int32_t *order, void *stream) {
+  const char *fn = "pst_group_cells_by_row";
+  PST_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && P > 0, fn, "need 0 <= n < 2^31 and P > 0");
+  if (n == 0) return 0;
+  PST_REQUIRE(row_of_cell && bins && order, fn, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(bins, 0, sizeof(uint32_t) * (size_t)P, st);
+  if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "memset failed"); }
+  const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)kNumSM * 8);
+  row_histogram_kernel<<<g, 256, 0, st>>>(row_of_cell, n, P, bins);
+  int rc = check_launch(fn);
+  if (rc) return rc;
+  row_scan_kernel<<<1, 1024, 0, st>>>(bins, P);
+  rc = check_launch(fn);
+  if (rc) return rc;
+  row_scatter_kernel<<<g, 256, 0, st>>>(row_of_cell, n, P, bins, order);
+  return check_launch(fn);
+}
+
+
 extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const int32_t *row_of_cell,
                                const float *scaling, const float *alpha, const float *beta_m1,
                                uint64_t seed, int64_t cell0, int64_t n, int32_t *X, int64_t ldx,
-                               uint32_t *flags, int32_t sampler, void *stream) {
+                               uint32_t *flags, int32_t sampler, const int32_t *cell_order,
+                               void *stream) {
   const char *fn = "pst_draw_counts";
   PST_REQUIRE(P >= 0 && G >= 0 && n >= 0 && cell0 >= 0, fn, "negative size");
   PST_REQUIRE(ldx >= G, fn, "ldx < G");
@@ -534,10 +605,10 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
     do {                                                                                                   \
       if (vec) draw_counts_hybrid_kernel<KF, true><<<hb, HY_THREADS, 0, st>>>(                             \
           PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
-          ldx, flags, mu_max, var_max);                                                                    \
+          ldx, flags, cell_order, mu_max, var_max);                                                        \
       else draw_counts_hybrid_kernel<KF, false><<<hb, HY_THREADS, 0, st>>>(                                \
           PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
-          ldx, flags, mu_max, var_max);                                                                    \
+          ldx, flags, cell_order, mu_max, var_max);                                                        \
     } while (0)
     switch (kfix) {
       case 4: PST_LAUNCH_HYBRID(4); break;

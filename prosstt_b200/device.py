@@ -4,6 +4,8 @@ Layout (include/prosstt_b200.h): branches in `tree.branches` order, branch b own
 rows [row_base[b], row_base[b]+T_b); P = sum T_b.  Everything here is small and
 replicated on every GPU (a few MB; the means table is P x G fp32); only cells shard.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -179,6 +181,8 @@ class CountEngine(object):
         self.alpha, self.beta_m1 = gene_params(alpha, beta, self.G, dev)
         self.sampler = nat.SAMPLERS[sampler]
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # status + scheduler scratch
+        self.group_rows = not os.environ.get("PST_NO_GROUP")    # developer switch
+        self._order = self._bins = None
 
     def draw(self, rows, scaling32, seed, cell0, out=None):
         """Sample X for the cells described by rows/scaling32 (device tensors); global
@@ -186,10 +190,20 @@ class CountEngine(object):
         n = int(rows.numel())
         if out is None:
             out = torch.empty((n, self.G), dtype=torch.int32, device=self.dev)
+        st = nat.stream_ptr(self.dev)
+        order = None
+        if self.group_rows and n >= 2048 and self.sampler == nat.SAMPLER_HYBRID:
+            # visit the cells grouped by tree row: concurrently running warps then share means rows
+            if self._order is None or self._order.numel() < n:
+                self._order = torch.empty(n, dtype=torch.int32, device=self.dev)
+                self._bins = torch.empty(max(1, self.P), dtype=torch.int32, device=self.dev)
+            order = self._order[:n]
+            nat.call("pst_group_cells_by_row", nat.ptr(rows), n, self.P, nat.ptr(self._bins),
+                     nat.ptr(order), st)
         nat.call("pst_draw_counts", nat.ptr(self.means), self.P, self.G, nat.ptr(rows),
                  nat.ptr(scaling32), nat.ptr(self.alpha), nat.ptr(self.beta_m1),
                  seed, int(cell0), n, out.data_ptr(), out.stride(0) if n else self.G,
-                 nat.ptr(self.flags), self.sampler, nat.stream_ptr(self.dev))
+                 nat.ptr(self.flags), self.sampler, order, st)
         return out
 
     def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None):
