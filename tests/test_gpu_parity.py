@@ -457,3 +457,106 @@ def test_reference_script_flow_and_restricted_sampler():
     fused = psim.add_non_diff_genes(X, 10, {"base_expr": np.full(10, 3.0), "alpha": np.full(10, 0.2),
                                             "beta": np.full(10, 2.0)}, scalings)
     assert fused.shape == (80, 510) and np.array_equal(fused[:, :500], X)
+
+
+# ------------------------------------------------------------------ sessions, named configs
+def test_density_session_equals_api_call():
+    """The resident session (bench path) and simulation.sample_density give the same bits."""
+    from prosstt_b200.session import DensitySession
+    t, s, d = _golden_tree("bp2")
+    N = 4099
+    sess = DensitySession(t, s["alpha"], s["beta"], N, device=DEV, sampler="hybrid")
+    sess.step(123)
+    Xs, pts, brs, scs = sess.results()
+    X, pt, br, sc = sim.sample_density(t, N, alpha=s["alpha"], beta=s["beta"], seed=123, device=DEV,
+                                       dtype=np.int32, sampler="hybrid")
+    assert np.array_equal(Xs, X) and np.array_equal(pts, pt) and list(brs) == list(br) and np.array_equal(scs, sc)
+    # a rank-local session (first = global index of its first cell) equals the matching shard
+    half = DensitySession(t, s["alpha"], s["beta"], N - N // 2, first=N // 2, device=DEV, sampler="hybrid")
+    half.step(123)
+    assert np.array_equal(half.results()[0], X[N // 2:])
+    host = torch.empty((N, t.G), dtype=torch.int32).pin_memory()
+    sess.step_to_host(123, host, chunk_cells=1000)
+    assert np.array_equal(host.numpy(), X)
+    # the row-grouped visiting order never changes the counts
+    sess.engine.group_rows = False
+    sess.step(123)
+    assert np.array_equal(sess.results()[0], X)
+
+
+def _bench_like_tree(bp, T, K, G, seed):
+    np.random.seed(seed)
+    top = [[int(a), int(b)] for a, b in ptree.Tree.gen_random_topology(bp)]
+    time = {b: T for b in range(2 * bp + 1)}
+    t = ptree.Tree(topology=top, time=time, num_branches=2 * bp + 1, branch_points=bp, modules=K, G=G)
+    rel, W, H = sim.simulate_lineage(t, a=0.05, seed=seed, device=DEV)
+    scale = sut.simulate_base_gene_exp(t, rel)
+    t.add_genes({b: np.exp(rel[b]) * scale for b in t.branches})
+    rng = np.random.RandomState(seed)
+    alpha = np.exp(rng.normal(np.log(0.2), np.log(1.5), size=G))
+    beta = np.exp(rng.normal(np.log(1.0), np.log(1.5), size=G)) + 1
+    return t, alpha, beta
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_config2_generate_simN_style_full_size(sampler):
+    """BASELINE config 2 at full size (5 branches x 50 steps, K=10, G=10 000, 10 000 cells via
+    sample_density = 1e8 counts), checked through size-independent properties: totals per gene and
+    per cell against the model mean/variance, zero fraction against (1+theta)^-r, sortedness of
+    nothing assumed, determinism, and sum-of-shards == whole."""
+    t, alpha, beta = _bench_like_tree(2, 50, 10, 10000, seed=5)
+    N = 10000
+    X, pt, br, sc = sim.sample_density(t, N, alpha=alpha, beta=beta, seed=9, device=DEV, dtype=np.int32,
+                                       sampler=sampler)
+    assert X.shape == (N, 10000) and X.min() >= 0
+    ot = orc.OTree(t.topology, dict(t.time), G=t.G)
+    ot.means = t.means
+    mu = orc.cell_means(ot, pt, list(br), sc)
+    var = alpha * mu ** 2 + beta * mu
+    zg = (X.sum(axis=0) - mu.sum(axis=0)) / np.sqrt(var.sum(axis=0))
+    zc = (X.sum(axis=1) - mu.sum(axis=1)) / np.sqrt(var.sum(axis=1))
+    assert abs(zg.mean()) < 0.05 and 0.9 < zg.std() < 1.1, (zg.mean(), zg.std())
+    assert abs(zc.mean()) < 0.05 and 0.9 < zc.std() < 1.1, (zc.mean(), zc.std())
+    theta = alpha * mu + beta - 1
+    p0 = np.exp(-mu / theta * np.log1p(theta))
+    assert abs((X == 0).mean() - p0.mean()) < 2e-4
+    # second moment: sum over cells of (x-mu)^2 / var ~ N per gene
+    chi = (((X - mu) ** 2) / var).sum(axis=0) / N
+    assert abs(np.median(chi) - 1) < 0.05, np.median(chi)
+    assert abs(int(X.sum()) - mu.sum()) < 6 * np.sqrt(var.sum())
+    shards = [sim.sample_density(t, N, alpha=alpha, beta=beta, seed=9, device=DEV, dtype=np.int32,
+                                 sampler=sampler, shard=(r, 4), out="torch")[0] for r in range(4)]
+    assert int(sum(int(x.sum(dtype=torch.int64).item()) for x in shards)) == int(X.sum())
+    assert torch.equal(torch.cat(shards).cpu(), torch.from_numpy(X))
+
+
+def test_config3_style_pseudotime_series_and_config5_style_streaming():
+    """Config 3 shape (10 branches, series sampler) and config 5 shape (many unequal branches,
+    streamed output) at reduced cell counts: index-map properties + streamed == resident."""
+    np.random.seed(11)
+    top = [[int(a), int(b)] for a, b in ptree.Tree.gen_random_topology(4)] + [[8, 9]]   # 9 + 1 chained = 10
+    time = {b: 30 + 5 * b for b in range(10)}
+    t = ptree.Tree(topology=top, time=time, num_branches=10, branch_points=4, modules=6, G=2000)
+    rel, W, H = sim.simulate_lineage(t, a=0.05, seed=3, device=DEV)
+    t.add_genes({b: np.exp(rel[b]) * sut.simulate_base_gene_exp(t, rel) for b in t.branches})
+    mt = t.get_max_time()
+    pts = [0, mt // 4, mt // 2, mt - 1]
+    X, pt, br, sc = sim.sample_pseudotime_series(t, 20000, pts, [4.0, 6.0, 8.0, 5.0], seed=4, device=DEV,
+                                                 dtype=np.int32)
+    assert X.shape == (20000, 2000) and pt.min() >= 0 and pt.max() <= mt - 1
+    bt = t.branch_times()
+    lo = np.array([bt[b][0] for b in br])
+    hi = np.array([bt[b][1] for b in br])
+    assert np.all((pt >= lo) & (pt <= hi))                    # every cell sits on its branch
+    for k, p in enumerate(pts):                              # cells cluster around their sample point
+        seg = pt[k * 5000:(k + 1) * 5000]
+        assert abs(seg.mean() - min(max(p, 0), mt - 1)) < 4.0
+    # streamed output over a many-branch tree equals the resident result and its checksum
+    from prosstt_b200.session import DensitySession
+    sess = DensitySession(t, 0.3, 2.0, 30000, device=DEV)
+    sess.step(8)
+    ref = sess.X.clone()
+    host = torch.empty((30000, 2000), dtype=torch.int32).pin_memory()
+    sess.step_to_host(8, host, chunk_cells=4096)
+    assert torch.equal(host, ref.cpu())
+    assert int(host.sum(dtype=torch.int64)) == int(ref.sum(dtype=torch.int64))

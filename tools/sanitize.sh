@@ -1,0 +1,8 @@
+#!/bin/bash
+# developer tool: compute-sanitizer over the count kernels and the lineage/index kernels (small sizes)
+for tool in memcheck racecheck; do
+  echo "== $tool: sampler_bench (both samplers, 1500 cells x 20000 genes)"
+  compute-sanitizer --tool $tool --print-limit 5 python tools/sampler_bench.py --cells 1500 --reps 1 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Invalid|^hybrid|^gamma" | head -12
+done
+echo "== memcheck: lineage + index-map tests"
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -q -x -k "walks or index_maps or pick_branch or pearson or nb_params or domain" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Invalid" | head
