@@ -122,6 +122,10 @@ def means_table(tree, tables, dev):
     if tree.means is None:
         raise ValueError("the tree has no mean expression yet: call add_genes() or "
                          "default_gene_expression() first")
+    if hasattr(tree.means, "table32"):                 # simulation.DeviceMeans: already in HBM
+        if tree.means.table32.device == dev and tuple(tree.means.table32.shape) == (tables.P, int(tree.G)):
+            return tree.means.table32
+        return tree.means.table32.to(dev)
     key = ("means32", str(dev), id(tree.means)) + tuple(id(tree.means[b]) for b in tables.names)
     cache = tree.__dict__.setdefault("_device_cache", {})
     hit = cache.get(key)

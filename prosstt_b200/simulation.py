@@ -148,7 +148,7 @@ class _LineageState(object):
 
 
 def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_tol=0,
-                     seed=None, device=None, max_attempts=10000, **kwargs):
+                     seed=None, device=None, max_attempts=10000, _return_state=False, **kwargs):
     """Relative mean expression of every gene at every tree position
     (simulation.py:215-286).  Branches are visited breadth first; each gets K momentum
     walks (device scan), is shifted to start where its parent ended, and rel = W.H is
@@ -189,6 +189,8 @@ def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_
             if all(diverges):
                 break
             del done[b]
+    if _return_state:
+        return state, H
     rel_host = state.rel.cpu().numpy()
     W_host = state.W.cpu().numpy()[:, :K]
     rel_means, programs = {}, {}
@@ -198,6 +200,79 @@ def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_
         rel_means[branch] = rel_host[lo:hi]
         programs[branch] = W_host[lo:hi]
     return pd.Series(rel_means), pd.Series(programs), H
+
+
+class DeviceMeans(object):
+    """`tree.means` kept on the GPU: the fp32 (P, G) table the samplers read, plus W, H and the
+    gene scale from which a branch's fp64 (T_b, G) array is rebuilt on the device and copied to
+    the host the first time `tree.means[branch]` is read.  Behaves like the reference's dict."""
+
+    def __init__(self, tables, W, H, gene_scale, table32):
+        self.tables, self.W, self.H, self.gene_scale, self.table32 = tables, W, H, gene_scale, table32
+        self._host = {}
+
+    def __getitem__(self, branch):
+        b = branch.item() if hasattr(branch, "item") else branch
+        if b not in self._host:
+            i = self.tables.index[b]
+            lo, T = int(self.tables.row_base[i]), int(self.tables.T[i])
+            K, G = self.H.shape
+            buf = torch.empty((T, G), dtype=torch.float64, device=self.W.device)
+            # pst_rel_means indexes its outputs from packed row 0: shift the pointer back by lo rows
+            nat.call("pst_rel_means", nat.ptr(self.W), nat.ptr(self.H), nat.ptr(self.gene_scale), lo, T, K, G,
+                     None, buf.data_ptr() - lo * G * 8, None, None, nat.stream_ptr(self.W.device))
+            self._host[b] = buf.cpu().numpy()
+        return self._host[b]
+
+    def keys(self):
+        return list(self.tables.names)
+
+    def __iter__(self):
+        return iter(self.tables.names)
+
+    def __len__(self):
+        return len(self.tables.names)
+
+    def __contains__(self, b):
+        return b in self.tables.index
+
+    def items(self):
+        return [(b, self[b]) for b in self.tables.names]
+
+    def values(self):
+        return [self[b] for b in self.tables.names]
+
+
+def default_gene_expression_on_device(tree, seed=None, device=None, abs_max=5000, gene_mean=0.8,
+                                      gene_std=1, **kwargs):
+    """simulate_lineage + simulate_base_gene_exp + exp(rel)*scale + add_genes (tree.py:436-446)
+    without the host round trip of the (P, G) tables: the per-gene maximum comes from the device,
+    the O(G) base-expression draw stays on the host (global legacy stream, reference draw order),
+    and the means table is built in HBM.  Sets tree.means to a DeviceMeans.  Returns
+    (H, gene_scale)."""
+    kwargs.setdefault("a", 0.05)
+    state, H = simulate_lineage(tree, seed=seed, device=device, _return_state=True, **kwargs)
+    dev, tb = state.dev, state.tables
+    st = nat.stream_ptr(dev)
+    # max over the tree of exp(rel) per gene (sim_utils.py:406-426,461): exp is monotone
+    cap = torch.exp(state.rel.max(dim=0).values).cpu().numpy()
+    base = np.zeros(tree.G)
+    for gene in range(tree.G):                                   # sim_utils.py:463-469
+        value = np.exp(np.random.normal(gene_mean, gene_std))
+        tries = 0
+        while value * cap[gene] > abs_max:
+            tries += 1
+            if tries > 100000:
+                raise RuntimeError("gene %d cannot satisfy abs_max=%g" % (gene, abs_max))
+            value = np.exp(np.random.normal(gene_mean, gene_std))
+        base[gene] = value
+    scale = nat.to_dev(base, torch.float64, dev)
+    table32 = torch.empty((tb.P, state.G), dtype=torch.float32, device=dev)
+    nat.call("pst_rel_means", nat.ptr(state.W), nat.ptr(state.H), nat.ptr(scale), 0, tb.P, state.K, state.G,
+             None, None, nat.ptr(table32), None, st)
+    tree.means = DeviceMeans(tb, state.W, state.H, scale, table32)
+    tree.invalidate_device_cache()
+    return H, base
 
 
 # =============================================================================== samplers

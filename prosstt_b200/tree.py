@@ -198,9 +198,8 @@ class Tree(object):
         return {p: top[top[:, 0] == p, 1] for p in np.unique(top[:, 0])}
 
     def default_gene_expression(self):
-        """simulate_lineage(a=0.05) + base expression + add_genes (tree.py:436-446)."""
+        """simulate_lineage(a=0.05) + base expression + add_genes (tree.py:436-446).  The (P, G)
+        tables stay in HBM; tree.means is a dict-like that copies a branch to the host on first
+        access (simulation.DeviceMeans)."""
         from prosstt_b200 import simulation as sim
-        from prosstt_b200 import sim_utils as sut
-        relative_expr, _, _ = sim.simulate_lineage(self, a=0.05)
-        gene_scale = sut.simulate_base_gene_exp(self, relative_expr)
-        self.add_genes({b: np.exp(relative_expr[b]) * gene_scale for b in self.branches})
+        sim.default_gene_expression_on_device(self, a=0.05)

@@ -560,3 +560,28 @@ def test_config3_style_pseudotime_series_and_config5_style_streaming():
     sess.step_to_host(8, host, chunk_cells=4096)
     assert torch.equal(host, ref.cpu())
     assert int(host.sum(dtype=torch.int64)) == int(ref.sum(dtype=torch.int64))
+
+
+def test_device_resident_means():
+    """Tree.default_gene_expression keeps the (P,G) tables in HBM; tree.means still reads like the
+    reference's dict of fp64 arrays and equals exp(W.H)*scale."""
+    np.random.seed(3)
+    t = ptree.Tree(topology=[[0, 1], [0, 2], [1, 3]], time={0: 20, 1: 35, 2: 9, 3: 50}, num_branches=4,
+                   branch_points=1, modules=7, G=1500)
+    H, scale = sim.default_gene_expression_on_device(t, seed=5, device=DEV)
+    assert isinstance(t.means, sim.DeviceMeans) and len(t.means) == 4 and list(t.means.keys()) == [0, 1, 2, 3]
+    tb = t.means.tables
+    W = t.means.W.cpu().numpy()
+    for i, b in enumerate(t.branches):
+        lo = int(tb.row_base[i])
+        want = np.exp(np.dot(W[lo:lo + t.time[b]], H)) * scale
+        assert t.means[b].shape == (t.time[b], 1500)
+        assert np.allclose(t.means[b], want, rtol=1e-10, atol=0)
+        assert np.all(t.means[b] <= 5000 * (1 + 1e-9))              # abs_max honoured
+        assert np.allclose(t.means.table32[lo:lo + t.time[b]].cpu().numpy(), want, rtol=2e-7, atol=0)
+    X, pt, br, sc = sim.sample_whole_tree(t, 3, seed=1, device=DEV)
+    assert X.shape == (3 * 114, 1500)
+    t2 = ptree.Tree(topology=t.topology, time=dict(t.time), num_branches=4, branch_points=1, modules=7, G=1500)
+    t2.add_genes({b: t.means[b] for b in t.branches})               # host dict of the same means
+    X2 = sim.sample_whole_tree(t2, 3, seed=1, device=DEV)[0]
+    assert np.array_equal(X, X2)

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Bit-exactness across GPU partitions on real multi-GPU hardware (run under torchrun).
+
+Every rank samples its shard of one sample_density / sample_whole_tree / sample_pseudotime_series
+call on its own GPU; rank 0 additionally samples the whole thing alone and compares the gathered
+shards with it bit for bit (NCCL all_gather of the slabs = the optional epilogue of DESIGN.md §5)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from prosstt_b200 import simulation as sim  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+import argparse
+a = argparse.Namespace(branch_points=3, steps_per_branch=40, programs=8, genes=4000)
+tree = bench.build_tree_gpu(a, dev)
+alpha, beta = bench.gene_hyper(a.genes)
+ok = True
+for name, call in (
+    ("sample_density", lambda **kw: sim.sample_density(tree, 8 * 1000 + 3, alpha=alpha, beta=beta, seed=5, device=dev, out="torch", **kw)),
+    ("sample_whole_tree", lambda **kw: sim.sample_whole_tree(tree, 5, alpha=alpha, beta=beta, seed=6, device=dev, out="torch", **kw)),
+    ("sample_pseudotime_series", lambda **kw: sim.sample_pseudotime_series(tree, [3000, 2001, 1000], [0, 40, 100], [3.0, 5.0, 8.0], alpha=alpha, beta=beta, seed=7, device=dev, out="torch", **kw)),
+):
+    X, pt, codes, sc = call(shard=(rank, world))
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([X.shape[0]], device=dev))
+    pad = int(max(s.item() for s in sizes))
+    mine = torch.zeros((pad, X.shape[1]), dtype=torch.int32, device=dev)
+    mine[:X.shape[0]] = X
+    slabs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(slabs, mine)                               # NCCL over NVLink
+    if rank == 0:
+        whole = call()[0]
+        gathered = torch.cat([s[:int(n.item())] for s, n in zip(slabs, sizes)])
+        same = torch.equal(gathered, whole)
+        ok &= same
+        print("%-26s world=%d cells=%d genes=%d  gathered shards == single-GPU result: %s  (sum %d)"
+              % (name, world, whole.shape[0], whole.shape[1], same, int(whole.sum(dtype=torch.int64))), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
