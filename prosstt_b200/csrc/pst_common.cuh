@@ -104,6 +104,14 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float *ptr, uint64_t policy)
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
   return v;
 }
+// 16-byte asynchronous global->shared copy (LDGSTS): a prefetch that holds no registers
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, uint64_t policy) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
+               :: "r"(s), "l"(gmem_src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void stg_i4_hint(int32_t *ptr, int4 v, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
                :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");

@@ -256,6 +256,7 @@ struct HyWarpQueues {
   float4 se[HY_QCAP];       // inversion tail: P(k), cdf(k)-u, a, q
   int2 sw[HY_QCAP];         //                 where the count goes: (cell, gene)
   float4 ge[HY_QCAP];       // mixture: mu, theta, cell, gene (ints bit-cast)
+  float4 mstage[32];        // next cell's means quad, filled by cp.async (one slot per lane)
 };
 
 // 1/k!, k = 0..16 (immediates after unrolling)
@@ -403,12 +404,22 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     int32_t row, row1; float s, s1;
     cell_scalars(cell, row, s);
     cell_scalars(cell1, row1, s1);
+    // means quad of the next cell: register load in the scalar path, cp.async into this lane's
+    // shared-memory slot in the vector path (a prefetch that survives the queue drains without
+    // occupying registers)
+    auto stage_means = [&](int32_t r) {
+      const int32_t rr = ((uint32_t)r < (uint64_t)P) ? r : 0;
+      cp_async16(&wq.mstage[lane], means + (int64_t)rr * G + g0, keep);
+      cp_async_commit();
+    };
     float4 mcur = load_means(row, g0);
     for (int ci = 0; ci < n_cells; ++ci) {
       const int32_t cell3 = cell_at(min(cell_lo + ci + 3, last_pos));
       int32_t row2; float s2;
       cell_scalars(cell2, row2, s2);
-      const float4 mnext = load_means(row1, g0);
+      float4 mnext;
+      if (VEC) stage_means(row1);                  // lands during this iteration
+      else mnext = load_means(row1, g0);
 
       // ---- this cell's quad
       const bool row_ok = (uint32_t)row < (uint64_t)P;
@@ -506,6 +517,10 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
       __syncwarp();
       // rotate the pipeline
+      if (VEC) {
+        cp_async_wait_all();                       // this lane's slot for cell ci+1 has landed
+        mnext = wq.mstage[lane];
+      }
       cell = cell1; row = row1; s = s1; cell1 = cell2; row1 = row2; s1 = s2; cell2 = cell3; mcur = mnext;
     }
   }
