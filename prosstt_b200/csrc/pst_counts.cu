@@ -397,28 +397,36 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         bm[j] = ok ? beta_m1[g0 + j] : 1.f;
       }
     }
-    // software pipeline: cell id three cells ahead, its scalars two ahead, its means one ahead
-    const int64_t last_pos = cell_lo + n_cells - 1;
-    int32_t cell = cell_at(cell_lo), cell1 = cell_at(min(cell_lo + 1, last_pos));
-    int32_t cell2 = cell_at(min(cell_lo + 2, last_pos));
-    int32_t row, row1; float s, s1;
-    cell_scalars(cell, row, s);
-    cell_scalars(cell1, row1, s1);
-    // means quad of the next cell: register load in the scalar path, cp.async into this lane's
-    // shared-memory slot in the vector path (a prefetch that survives the queue drains without
-    // occupying registers)
+    // Per-cell metadata (cell id, tree row, library size) is the same for every lane: lane l
+    // loads it for cell (group*32 + l) with one coalesced request per 32 cells and the loop
+    // broadcasts it with shuffles.  The means quad of the next cell is prefetched: register load
+    // in the scalar path, cp.async into this lane's shared-memory slot in the vector path (a
+    // prefetch that survives the queue drains without occupying registers).
+    int32_t meta_cell = 0, meta_row = 0; float meta_s = 1.f;
+    auto load_meta = [&](int first) {                       // cells first .. first+31 of this chunk
+      const int i = first + lane;
+      const int64_t pos = cell_lo + (i < n_cells ? i : n_cells - 1);
+      meta_cell = cell_order ? cell_order[pos] : (int32_t)pos;
+      meta_row = row_of_cell[meta_cell];
+      meta_s = scaling[meta_cell];
+    };
     auto stage_means = [&](int32_t r) {
       const int32_t rr = ((uint32_t)r < (uint64_t)P) ? r : 0;
       cp_async16(&wq.mstage[lane], means + (int64_t)rr * G + g0, keep);
       cp_async_commit();
     };
+    load_meta(0);
+    int32_t row = __shfl_sync(0xffffffffu, meta_row, 0);
     float4 mcur = load_means(row, g0);
     for (int ci = 0; ci < n_cells; ++ci) {
-      const int32_t cell3 = cell_at(min(cell_lo + ci + 3, last_pos));
-      int32_t row2; float s2;
-      cell_scalars(cell2, row2, s2);
+      const int src = ci & 31;
+      const int32_t cell = __shfl_sync(0xffffffffu, meta_cell, src);
+      const float s = __shfl_sync(0xffffffffu, meta_s, src);
+      // next cell's tree row (clamped at the end of the chunk), then its means quad
+      if (src == 31) load_meta(ci + 1);                     // warp-uniform branch, every 32 cells
+      const int32_t row1 = __shfl_sync(0xffffffffu, meta_row, (ci + 1 < n_cells) ? ((ci + 1) & 31) : src);
       float4 mnext;
-      if (VEC) stage_means(row1);                  // lands during this iteration
+      if (VEC) stage_means(row1);                           // lands during this iteration
       else mnext = load_means(row1, g0);
 
       // ---- this cell's quad
@@ -521,7 +529,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         cp_async_wait_all();                       // this lane's slot for cell ci+1 has landed
         mnext = wq.mstage[lane];
       }
-      cell = cell1; row = row1; s = s1; cell1 = cell2; row1 = row2; s1 = s2; cell2 = cell3; mcur = mnext;
+      row = row1; mcur = mnext;
     }
   }
   if (ns > 0) drain_search(0, ns);
