@@ -585,3 +585,36 @@ def test_device_resident_means():
     t2.add_genes({b: t.means[b] for b in t.branches})               # host dict of the same means
     X2 = sim.sample_whole_tree(t2, 3, seed=1, device=DEV)[0]
     assert np.array_equal(X, X2)
+
+
+def test_padded_row_stride_and_raw_abi_call():
+    """pst_draw_counts with ldx > G writes only the first G columns of each row and gives the same
+    counts as the dense call (the C ABI is called directly, as a foreign binding would)."""
+    t, s, d = _golden_tree("bp2")
+    dev = torch.device(DEV)
+    tb = TreeTables(t, dev)
+    eng = CountEngine(t, tb, s["alpha"], s["beta"], dev, sampler="hybrid")
+    n, G, ldx = 777, t.G, t.G + 12
+    rng = np.random.RandomState(4)
+    rows = _dev(rng.randint(0, tb.P, size=n), torch.int32)
+    sc = _dev(np.exp(rng.normal(0, 0.7, size=n)), torch.float32)
+    dense = eng.draw(rows, sc, 99, 5)
+    padded = torch.full((n, ldx), -7, dtype=torch.int32, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    for sampler in (nat.SAMPLER_HYBRID, nat.SAMPLER_GAMMA_POISSON):
+        padded.fill_(-7)
+        nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
+                 status, sampler, None, nat.stream_ptr(dev))
+        assert torch.all(padded[:, G:] == -7)
+        if sampler == nat.SAMPLER_HYBRID:
+            assert torch.equal(padded[:, :G], dense)
+        else:
+            assert abs(float(padded[:, :G].float().mean()) / float(dense.float().mean()) - 1) < 0.05
+    assert status.tolist() == [0, 0, 0, 0]                 # flags clear, scheduler words rearmed
+    # invalid arguments are reported through the status code / pst_last_error, not a crash
+    with pytest.raises(ValueError):
+        nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, G - 1,
+                 status, nat.SAMPLER_HYBRID, None, nat.stream_ptr(dev))
+    with pytest.raises(ValueError):
+        nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
+                 status, 7, None, nat.stream_ptr(dev))
