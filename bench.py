@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--branch-points", type=int, default=7, help="7 bifurcations = 15 branches")
     ap.add_argument("--steps-per-branch", type=int, default=50)
     ap.add_argument("--programs", type=int, default=10)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4: the headline config; c5: 50-branch tree, 1000 steps/branch, G=30000 (means table 6 GB)")
     ap.add_argument("--sampler", default=None)
     ap.add_argument("--e2e-cells", type=int, default=131072, help="cells per e2e step (host buffers)")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -54,9 +56,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def apply_workload(a):
+    if a.workload == "c5":        # BASELINE config 5 shape (many_branches_cells), cells per step as given
+        a.branch_points, a.steps_per_branch, a.genes = 25, 1000, 30000      # 51 branches
+
+
 def workload_name(a):
-    return ("C4 sample_density: %d-branch random binary tree x %d steps, K=%d, G=%d, %d cells/GPU"
-            % (2 * a.branch_points + 1, a.steps_per_branch, a.programs, a.genes, a.cells))
+    return ("%s sample_density: %d-branch random binary tree x %d steps, K=%d, G=%d, %d cells/GPU"
+            % (a.workload.upper(), 2 * a.branch_points + 1, a.steps_per_branch, a.programs, a.genes, a.cells))
 
 
 def gene_hyper(G):
@@ -82,6 +89,10 @@ def build_tree_gpu(a, dev):
     t = ptree.Tree(topology=top, time=time_, num_branches=len(time_), branch_points=a.branch_points,
                    modules=a.programs, G=a.genes)
     np.random.seed(SEEDS["lineage"])
+    if t.G * sum(time_.values()) > 5e7:
+        # big tables stay in HBM (no host round trip of the P x G arrays)
+        sim.default_gene_expression_on_device(t, seed=SEEDS["lineage"], device=dev)
+        return t
     rel, W, H = sim.simulate_lineage(t, a=0.05, seed=SEEDS["lineage"], device=dev)
     scale = sut.simulate_base_gene_exp(t, rel)
     t.add_genes({b: np.exp(rel[b]) * scale for b in t.branches})
@@ -273,8 +284,8 @@ def run_ours(a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "sampler": sampler, "output": "int32 (N,G) resident in HBM",
                    "seeds": SEEDS, "cells_per_gpu": a.cells, "genes": a.genes,
-                   "l2": "every step writes a %.1f GB count slab >> 126 MB L2 (self-flushing); the "
-                         "%.0f MB fp32 means table is meant to stay L2-resident"
+                   "l2": "every step writes a %.1f GB count slab >> 126 MB L2 (self-flushing); fp32 means "
+                         "table %.0f MB, cells visited grouped by tree row"
                          % (algo_bytes / 1e9, tree.G * sess.tables.P * 4 / 1e6)},
         "clocks": clock_rec, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -352,6 +363,7 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse_args()
+    apply_workload(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -103,8 +103,10 @@ int pst_rel_means(const double *W, const double *H, const double *gene_scale,
  * (sim_utils.py:145-168, 249-251).  out_count is one int32, caller zeroes it. */
 int pst_pearson_anticorr(const double *A, const double *B, int64_t nrows, int64_t G,
                          int32_t *out_count, void *stream);
-/* fp64 -> fp32 table conversion for means supplied by the user (tree.add_genes). */
-int pst_f64_to_f32(const double *in, int64_t n, float *out, void *stream);
+/* fp64 -> fp32 table conversion for means supplied by the user (tree.add_genes).  Positive
+ * values below min_positive (pass 1e-30; 0 disables) are raised to it so that a mean that is
+ * positive in fp64 never underflows to 0 in the fp32 table (pst_rel_means does the same). */
+int pst_f64_to_f32(const double *in, int64_t n, double min_positive, float *out, void *stream);
 
 /* ---- samplers' index maps: simulation.py:319-548, sim_utils.py:342-403 -------- */
 /* idx[i] = searchsorted(cdf, u[i], side='right') clipped to P-1; row_of_cell = idx

@@ -113,6 +113,7 @@ __global__ void walk_carry_kernel(int n_order, int K, const int32_t *__restrict_
 // a block owns 256 genes; the W rows of a tile sit in shared memory and are
 // broadcast; each thread keeps RT accumulators so one H load feeds RT FMAs.
 // ---------------------------------------------------------------------------
+constexpr double kMinPositiveMean = 1e-30;
 constexpr int RM_THREADS = 256;
 constexpr int RM_RT = 8;               // rows per register tile
 
@@ -152,7 +153,9 @@ rel_means_kernel(const double *__restrict__ W, const double *__restrict__ H,
           if (out_m64 || out_m32) {
             const double m = exp(acc[i]) * gs;
             if (out_m64) out_m64[o] = m;
-            if (out_m32) out_m32[o] = (float)m;
+            // a positive mean below the fp32 range would read as 0 (= scipy's domain error):
+            // keep it positive; the count is 0 with probability 1 - 1e-30 either way
+            if (out_m32) out_m32[o] = (m > 0.0 && m < kMinPositiveMean) ? (float)kMinPositiveMean : (float)m;
           }
         }
       }
@@ -184,10 +187,13 @@ __global__ void pearson_kernel(const double *__restrict__ A, const double *__res
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(out_count, __popc(m));
 }
 
-__global__ void f64_to_f32_kernel(const double *__restrict__ in, int64_t n, float *__restrict__ out) {
+__global__ void f64_to_f32_kernel(const double *__restrict__ in, int64_t n, double min_positive,
+                                  float *__restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = (float)in[i];
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = in[i];
+    out[i] = (v > 0.0 && v < min_positive) ? (float)min_positive : (float)v;
+  }
 }
 
 }  // namespace pst
@@ -270,12 +276,12 @@ extern "C" int pst_pearson_anticorr(const double *A, const double *B, int64_t nr
   return check_launch(fn);
 }
 
-extern "C" int pst_f64_to_f32(const double *in, int64_t n, float *out, void *stream) {
+extern "C" int pst_f64_to_f32(const double *in, int64_t n, double min_positive, float *out, void *stream) {
   const char *fn = "pst_f64_to_f32";
   PST_REQUIRE(n >= 0, fn, "negative size");
   if (n == 0) return 0;
   PST_REQUIRE(in && out, fn, "null pointer");
   const int64_t blocks = min((n + 255) / 256, (int64_t)kNumSM * 16);
-  f64_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, n, out);
+  f64_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, n, min_positive, out);
   return check_launch(fn);
 }

@@ -144,7 +144,7 @@ def means_table(tree, tables, dev):
             raise ValueError("means of branch %s have shape %s, expected %s"
                              % (str(b), tuple(m64.shape), (int(tables.T[i]), G)))
         dst = out[int(tables.row_base[i]):int(tables.row_base[i]) + int(tables.T[i])]
-        nat.call("pst_f64_to_f32", nat.ptr(m64), m64.numel(), dst.data_ptr(), st)
+        nat.call("pst_f64_to_f32", nat.ptr(m64), m64.numel(), 1e-30, dst.data_ptr(), st)
     cache.clear()
     cache[key] = out
     return out

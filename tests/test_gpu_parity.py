@@ -618,3 +618,47 @@ def test_padded_row_stride_and_raw_abi_call():
     with pytest.raises(ValueError):
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
                  status, 7, None, nat.stream_ptr(dev))
+
+
+def test_api_variants_from_the_notebooks():
+    """Call patterns listed in SURVEY.md 3.7: Newick trees with long string names, int `cells` and
+    scalar `point_std` for the time series, scale=False, scalar Poisson-limit alpha/beta, explicit
+    branches for _sample_data_at_times, density assigned directly."""
+    t = ptree.Tree.from_newick("(early_left:12,early_right:30)progenitor:20;", genes=300, modules=5)
+    assert t.branches == ["progenitor", "early_left", "early_right"]
+    np.random.seed(8)
+    sim.default_gene_expression_on_device(t, seed=2, device=DEV)
+    # long names are not truncated to the first name's length (reference bug, SURVEY Q6)
+    X, pt, br, sc = sim.sample_pseudotime_series(t, 90, [0, 25, 45], 6.0, seed=3, device=DEV)
+    assert X.shape == (90, 300) and set(br) <= set(t.branches) and "early_right" in set(br)
+    bt = t.branch_times()
+    assert all(bt[b][0] <= p <= bt[b][1] for p, b in zip(pt, br))
+    # int cells are split as int(cells / n_points) per point (Q7): 100 -> 3 x 33
+    X, pt, br, sc = sim.sample_pseudotime_series(t, 100, [0, 25, 45], [2.0, 2.0, 2.0], seed=3, device=DEV)
+    assert X.shape[0] == 99
+    # scale=False -> unit library sizes; Poisson limit alpha=0, beta=1+10e-9 (linear.ipynb cell 23)
+    X, pt, br, sc = sim.sample_whole_tree(t, 40, alpha=0, beta=1 + 10e-9, scale=False, seed=4, device=DEV)
+    assert np.all(sc == 1.0) and X.shape == (40 * 62, 300)
+    mu = np.stack([t.means[b][p - bt[b][0]] for p, b in zip(pt, br)])
+    z = (X.sum(axis=0) - mu.sum(axis=0)) / np.sqrt(mu.sum(axis=0))          # Poisson: var == mean
+    assert abs(z.mean()) < 0.3 and 0.8 < z.std() < 1.2, (z.mean(), z.std())
+    # explicit branches and a density dict assigned directly (density_sampling.ipynb cell 8)
+    X2, pt2, br2, sc2 = sim._sample_data_at_times(t, pt[:50], branches=br[:50], alpha=0.2, beta=2.0, seed=5, device=DEV)
+    assert list(br2) == list(br[:50]) and np.array_equal(pt2, pt[:50])
+    dens = {b: np.linspace(1, 2, t.time[b]) for b in t.branches}
+    tot = sum(v.sum() for v in dens.values())
+    t.density = {b: v / tot for b, v in dens.items()}
+    X3, pt3, br3, sc3 = sim.sample_density(t, 5000, seed=6, device=DEV)
+    late = np.mean([p - bt[b][0] >= t.time[b] / 2 for p, b in zip(pt3, br3)])
+    assert 0.55 < late < 0.62                                   # linear density: 7/12 of the mass is late
+    with pytest.raises(ValueError):                             # density that does not sum to one
+        t.density = {b: v for b, v in dens.items()}
+        sim.sample_density(t, 10, seed=6, device=DEV)
+
+
+def test_means_below_fp32_range_stay_positive():
+    """A mean that is positive in fp64 but below the fp32 range must not turn into scipy's domain
+    error: the table keeps it at 1e-30 and the count is 0 (long branches drive exp(rel) to 1e-50)."""
+    t = _flat_tree([1e-50, 3.0, 1e-320, 2.0])
+    X = sim.draw_counts(t, np.zeros(1000, int), [0] * 1000, np.full(1000, 0.01), 0.2, 2.0, seed=1, device=DEV)
+    assert np.all(X[:, 0] == 0) and np.all(X[:, 2] == 0) and X[:, 1].sum() > 0
