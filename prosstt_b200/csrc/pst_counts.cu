@@ -350,22 +350,16 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   const uint32_t n_strips = (Q + 31u) / 32u;
   // cells are visited in `cell_order` (grouped by tree row so that concurrently running warps
   // share means rows in L2/L1); results do not depend on the order
-#ifdef HY_NO_ORDER
-  auto cell_at = [&](int64_t pos) -> int32_t { return (int32_t)pos; };
-#else
-  auto cell_at = [&](int64_t pos) -> int32_t { return cell_order ? cell_order[pos] : (int32_t)pos; };
-#endif
-  auto cell_scalars = [&](int32_t cell, int32_t &row, float &s) {
-    row = row_of_cell[cell];
-    s = scaling[cell];
-  };
   auto load_means = [&](int32_t row, uint32_t g0) -> float4 {
     const int32_t r = ((uint32_t)row < (uint64_t)P) ? row : 0;       // bad rows are flagged at use
-    if (VEC) return ldg_f4_hint(means + (int64_t)r * G + g0, keep);
-    float m[4];
+    if constexpr (VEC) {
+      return ldg_f4_hint(means + (int64_t)r * G + g0, keep);
+    } else {
+      float m[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = ((int64_t)g0 + j < G) ? means[(int64_t)r * G + g0 + j] : 1.f;
-    return make_float4(m[0], m[1], m[2], m[3]);
+      for (int j = 0; j < 4; ++j) m[j] = ((int64_t)g0 + j < G) ? means[(int64_t)r * G + g0 + j] : 1.f;
+      return make_float4(m[0], m[1], m[2], m[3]);
+    }
   };
 
   // chunks are handed out dynamically (flags[1] is the next-chunk counter): warps whose
@@ -627,11 +621,19 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
   if (sampler == PST_SAMPLER_HYBRID) {
-    // developer knobs (profiling only; they change the bit stream, never set them in production)
+    // The route thresholds and the head length are part of the sampler's definition (they decide
+    // which uniforms a count consumes).  A developer build (-DPST_DEV_KNOBS, tools/tune_hybrid.sh)
+    // can override them from the environment for profiling sweeps; the product build cannot.
+#ifdef PST_DEV_KNOBS
     static const int kfix = getenv("PST_HY_KFIX") ? atoi(getenv("PST_HY_KFIX")) : HY_KFIX;
     static const float mu_max = getenv("PST_HY_MU_MAX") ? (float)atof(getenv("PST_HY_MU_MAX")) : HY_MU_MAX;
     static const float var_max = getenv("PST_HY_VAR_MAX") ? (float)atof(getenv("PST_HY_VAR_MAX")) : HY_VAR_MAX;
     static const int ctas_per_sm = getenv("PST_HY_CTAS") ? atoi(getenv("PST_HY_CTAS")) : HY_MIN_CTAS;
+#else
+    const int kfix = HY_KFIX;
+    const float mu_max = HY_MU_MAX, var_max = HY_VAR_MAX;
+    const int ctas_per_sm = HY_MIN_CTAS;
+#endif
     const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * ((Q + 31) / 32);
     PST_REQUIRE(n_chunks < ((int64_t)1 << 31), fn, "too many work chunks in one call (chunk the cells)");
     const int64_t need = (n_chunks + HY_WARPS - 1) / HY_WARPS;
@@ -646,14 +648,17 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
           PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
           ldx, flags, cell_order, mu_max, var_max);                                                        \
     } while (0)
+#ifdef PST_DEV_KNOBS
     switch (kfix) {
-      case 4: PST_LAUNCH_HYBRID(4); break;
       case 6: PST_LAUNCH_HYBRID(6); break;
       case 8: PST_LAUNCH_HYBRID(8); break;
       case 12: PST_LAUNCH_HYBRID(12); break;
-      case 16: PST_LAUNCH_HYBRID(16); break;
       default: PST_LAUNCH_HYBRID(HY_KFIX); break;
     }
+#else
+    (void)kfix;
+    PST_LAUNCH_HYBRID(HY_KFIX);
+#endif
 #undef PST_LAUNCH_HYBRID
     return check_launch(fn);
   }

@@ -1,5 +1,9 @@
 #!/bin/bash
+# developer tool (GPU box): sweep the hybrid sampler's knobs.  Needs a developer build:
+#   PST_NVCC_DEFS="-DPST_DEV_KNOBS" python prosstt_b200/build.py --force
 run() { echo "== $*"; env "$@" python tools/sampler_bench.py --cells 200000 --samplers hybrid --reps 3 2>&1 | grep -E "^hybrid|rror"; }
-inst() { env "$@" ncu --metrics smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:draw_counts_hybrid -s 1 -c 1 python tools/sampler_bench.py --cells 200000 --samplers hybrid --reps 1 2>&1 | grep -E "smsp__"; }
-for l in old new old new; do run PST_LIB=tools/lib_$l.so; done
-for l in old new; do echo "== inst $l"; inst PST_LIB=tools/lib_$l.so; done
+run PST_HY_KFIX=8
+run PST_HY_KFIX=10
+run PST_HY_KFIX=12
+run PST_HY_MU_MAX=24 PST_HY_VAR_MAX=300
+run PST_HY_MU_MAX=48 PST_HY_VAR_MAX=900
