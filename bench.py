@@ -202,7 +202,10 @@ def run_ours(a):
         torch.cuda.synchronize(dev)
 
     sampler = a.sampler or sim.DEFAULT_SAMPLER
+    t_setup = time.perf_counter()
     tree = build_tree_gpu(a, dev)
+    torch.cuda.synchronize(dev)
+    setup_s = time.perf_counter() - t_setup     # Tree + simulate_lineage + base expression + means (untimed set-up)
     alpha, beta = gene_hyper(a.genes)
     sess = DensitySession(tree, alpha, beta, a.cells, first=rank * a.cells, device=dev, sampler=sampler)
     seed = SEEDS["sampling"]
@@ -284,6 +287,7 @@ def run_ours(a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "sampler": sampler, "output": "int32 (N,G) resident in HBM",
                    "seeds": SEEDS, "cells_per_gpu": a.cells, "genes": a.genes,
+                   "tree_lineage_means_setup_s": round(setup_s, 3),
                    "l2": "every step writes a %.1f GB count slab >> 126 MB L2 (self-flushing); fp32 means "
                          "table %.0f MB, cells visited grouped by tree row"
                          % (algo_bytes / 1e9, tree.G * sess.tables.P * 4 / 1e6)},

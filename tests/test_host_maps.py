@@ -183,3 +183,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_text_writers_round_trip(tmp_path):
+    """tree_utils.save_* write the reference's file set (tree_utils.py:59-173)."""
+    import pandas as pd
+    X = np.arange(12).reshape(3, 4)
+    uMs = {"A": np.ones((2, 4)) * 0.5, "B": np.zeros((1, 4))}
+    H = np.arange(8.0).reshape(2, 4)
+    tu.save_matrices("job", str(tmp_path), X, uMs, H)
+    tu.save_cell_params("job", str(tmp_path), [0, 1, 2], ["A", "A", "B"], [1.0, 0.5, 2.0])
+    tu.save_gene_params("job", str(tmp_path), [1.0, 2, 3, 4], [0.1, 0.2, 0.3, 0.4], [2.0, 2, 2, 2])
+    t = ptree.Tree(modules=3, G=4)
+    tu.save_params("job", str(tmp_path), t, 7)
+    back = pd.read_csv(tmp_path / "job_simulation.txt", sep="\t", index_col=0)
+    assert list(back.columns) == ["gene_%d" % i for i in range(4)] and list(back.index) == ["cell_0", "cell_1", "cell_2"]
+    assert np.array_equal(back.values, X)
+    assert np.array_equal(np.loadtxt(tmp_path / "job_h.txt"), H)
+    assert np.array_equal(np.loadtxt(tmp_path / "job_umsA.txt"), uMs["A"])
+    cells = pd.read_csv(tmp_path / "job_cellparams.txt", sep="\t", index_col=0)
+    assert list(cells.columns) == ["pseudotime", "branches", "scalings"] and list(cells["branches"]) == ["A", "A", "B"]
+    genes = pd.read_csv(tmp_path / "job_geneparams.txt", sep="\t", index_col=0)
+    assert list(genes.columns) == ["alpha", "beta", "genescale"]
+    text = (tmp_path / "job_params.txt").read_text()
+    assert "Genes: 4" in text and "#modules: 3" in text and text.endswith("random seed: 7")
