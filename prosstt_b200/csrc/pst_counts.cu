@@ -251,6 +251,10 @@ constexpr int HY_KMAX = 2048;                // hard bound on inversion terms
 #endif
 constexpr float HY_MU_MAX = 32.0f, HY_VAR_MAX = 400.0f;   // route: mean <= 32 and sd <= 20
 constexpr int HY_KFIX = 10;                                  // unrolled head terms
+// The tail's frozen-cdf guard (pp <= 2e-8 -> stop counting) assumes it can only trigger past the
+// mode: for every routed (mu, theta) the pmf at k >= HY_KFIX-1 is above 2e-8 until the mode.  The
+// smallest such value is Poisson(32) at k = 9: 1.2e-6.  Larger HY_MU_MAX would break that.
+static_assert(HY_MU_MAX <= 32.0f && HY_KFIX >= 10, "frozen-cdf guard needs P(k>=KFIX-1) > 2e-8 before the mode");
 
 struct HyWarpQueues {
   float4 se[HY_QCAP];       // inversion tail: P(k), cdf(k)-u, a, q

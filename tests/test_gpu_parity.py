@@ -662,3 +662,39 @@ def test_means_below_fp32_range_stay_positive():
     t = _flat_tree([1e-50, 3.0, 1e-320, 2.0])
     X = sim.draw_counts(t, np.zeros(1000, int), [0] * 1000, np.full(1000, 0.01), 0.2, 2.0, seed=1, device=DEV)
     assert np.all(X[:, 0] == 0) and np.all(X[:, 2] == 0) and X[:, 1].sum() > 0
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_large_sample_goodness_of_fit(sampler):
+    """2e7 draws per regime (histogrammed on the GPU) against the exact pmf: resolves relative pmf
+    errors of ~1e-3, i.e. the fp32 / MUFU approximations and the route boundaries of the hybrid
+    sampler (mu = 32, variance = 400)."""
+    import scipy.stats
+    regimes = [(0.3, 0.3, 2.0), (1.8, 0.2, 2.0), (6.0, 0.25, 1.6), (14.0, 0.1, 2.5), (31.9, 0.05, 1.5),
+               (32.1, 0.05, 1.5), (20.0, 0.9, 2.0), (19.0, 1.0, 2.0)]        # last two straddle var = 400
+    mu = np.array([r[0] for r in regimes]); alpha = np.array([r[1] for r in regimes]); beta = np.array([r[2] for r in regimes])
+    N = 20000000
+    t = _flat_tree(mu)
+    dev = torch.device(DEV)
+    eng = CountEngine(t, TreeTables(t, dev), alpha, beta, dev, sampler=sampler)
+    X = eng.draw(torch.zeros(N, dtype=torch.int32, device=dev), torch.ones(N, dtype=torch.float32, device=dev), 4242, 0)
+    eng.check()
+    theta = alpha * mu + beta - 1
+    r, p = mu / theta, 1 / (1 + theta)
+    for g in range(len(regimes)):
+        hist = torch.bincount(X[:, g].long()).cpu().numpy().astype(float)
+        hi = int(scipy.stats.nbinom.ppf(1 - 1e-6, r[g], p[g]))
+        pmf = scipy.stats.nbinom.pmf(np.arange(hi + 1), r[g], p[g])
+        obs = np.zeros(hi + 2)
+        k = min(len(hist), hi + 1)
+        obs[:k] = hist[:k]
+        obs[hi + 1] = hist[hi + 1:].sum() if len(hist) > hi + 1 else 0
+        exp = np.append(pmf, max(1 - pmf.sum(), 0)) * N
+        keep = exp >= 50
+        o = np.append(obs[keep], obs[~keep].sum()); e = np.append(exp[keep], exp[~keep].sum())
+        if e[-1] < 1:
+            o, e = o[:-1], e[:-1]
+        chi2 = ((o - e) ** 2 / e).sum()
+        pval = scipy.stats.chi2.sf(chi2, len(e) - 1)
+        assert pval > 1e-6, (regimes[g], chi2, len(e), pval)
+        assert abs(X[:, g].double().mean().item() - mu[g]) < 5 * np.sqrt((alpha[g] * mu[g] ** 2 + beta[g] * mu[g]) / N)
