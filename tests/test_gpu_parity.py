@@ -698,3 +698,30 @@ def test_large_sample_goodness_of_fit(sampler):
         pval = scipy.stats.chi2.sf(chi2, len(e) - 1)
         assert pval > 1e-6, (regimes[g], chi2, len(e), pval)
         assert abs(X[:, g].double().mean().item() - mu[g]) < 5 * np.sqrt((alpha[g] * mu[g] ** 2 + beta[g] * mu[g]) / N)
+
+
+def test_density_index_matches_numpy_searchsorted_at_scale():
+    """pst_density_index == np.searchsorted(cdf, u, side='right') bit for bit on a 50 000-position
+    cdf with flat stretches (zero-density positions), plus the row-grouping permutation."""
+    rng = np.random.RandomState(12)
+    P, n = 50000, 1000000
+    p = rng.gamma(0.3, size=P)
+    p[rng.randint(0, P, size=5000)] = 0.0                       # repeated cdf values
+    p /= p.sum()
+    from prosstt_b200.device import choice_cdf
+    cdf = choice_cdf(p)
+    u = rng.random_sample(n)
+    u[:3] = [0.0, cdf[17], np.nextafter(1.0, 0.0)]              # exact hits and the ends
+    dev = torch.device(DEV)
+    rows = torch.empty(n, dtype=torch.int32, device=dev)
+    nat.call("pst_density_index", _dev(cdf, torch.float64), P, _dev(u, torch.float64), n, None, None, rows, None, None,
+             nat.stream_ptr(dev))
+    want = np.searchsorted(cdf, u, side="right")
+    assert np.array_equal(rows.cpu().numpy(), np.minimum(want, P - 1))
+    # cells grouped by row: a permutation, non-decreasing in row
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    bins = torch.empty(P, dtype=torch.int32, device=dev)
+    nat.call("pst_group_cells_by_row", rows, n, P, bins, order, nat.stream_ptr(dev))
+    o = order.cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(n))
+    assert np.all(np.diff(rows.cpu().numpy()[o]) >= 0)
