@@ -247,19 +247,23 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         ecells = min(a.e2e_cells, a.cells)
-        es = DensitySession(tree, alpha, beta, ecells, first=rank * ecells, device=dev, sampler=sampler,
-                            resident_output=False)
         hX = torch.empty((ecells, a.genes), dtype=torch.int32).pin_memory()
         hpt = torch.empty(ecells, dtype=torch.int64).pin_memory()
         hco = torch.empty(ecells, dtype=torch.int32).pin_memory()
         hsc = torch.empty(ecells, dtype=torch.float64).pin_memory()
-        h2d = es.upload_inputs()
-        d2h = es.step_to_host(seed, hX, hpt, hco, hsc)        # warm-up
+        h2d = 16 * sess.tables.P + 8 * a.genes    # per call: cdf f64 + pos_pt/pos_branch i32 [P], alpha/beta-1 f32 [G]
+        d2h = hX.numel() * 4 + ecells * (8 + 4 + 8)
+
+        def api_call(seed_):
+            # the reference-facing call: sample_density(tree, no_cells, alpha, beta) with host outputs
+            return sim.sample_density(tree, ecells * world, alpha=alpha, beta=beta, seed=seed_, device=dev,
+                                      shard=(rank, world), dtype=np.int32, sampler=sampler,
+                                      host_out=(hX, hpt, hco, hsc))
+        api_call(seed)                                        # warm-up
         barrier()
         t0 = time.perf_counter()
         for i in range(a.e2e_steps):
-            h2d = es.upload_inputs()
-            d2h = es.step_to_host(seed + 200 + i, hX, hpt, hco, hsc)
+            Xh, pth, brh, sch = api_call(seed + 200 + i)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -269,9 +273,10 @@ def run_ours(a):
         e2e = {"value": float(ecells) * a.genes * world * a.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "cells_per_step_per_gpu": ecells, "steps": a.e2e_steps,
-               "note": "DensitySession.step_to_host: per-call inputs uploaded, int32 counts + pt + "
-                       "branch + scalings copied to pinned host buffers in overlapped chunks"}
-        del hX, es
+               "note": "simulation.sample_density(tree, N, alpha, beta, host_out=pinned buffers): tree tables, "
+                       "cdf and gene parameters uploaded per call; int32 counts + pseudotime + branch + "
+                       "scalings land in host memory (chunked, copy overlapped with sampling)"}
+        del hX
 
     if rank != 0:
         if world > 1:

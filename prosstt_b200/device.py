@@ -215,13 +215,22 @@ class CountEngine(object):
         tensor, ideally pinned): sampling of chunk i+1 overlaps the copy of chunk i."""
         n = int(rows.numel())
         if chunk_cells is None:
-            chunk_cells = max(1, min(n, (256 << 20) // max(1, 4 * self.G)))
+            # ~1 GiB copies keep the copy engine at its large-transfer rate; the first chunks are
+            # smaller so that the device->host stream starts almost immediately
+            chunk_cells = max(1, min(n, (1 << 30) // max(1, 4 * self.G)))
+            ramp = [max(1, chunk_cells // 8), max(1, chunk_cells // 4), max(1, chunk_cells // 2)]
+        else:
+            ramp = []
+        bounds, lo = [], 0
+        while lo < n:
+            size = ramp.pop(0) if ramp else chunk_cells
+            bounds.append((lo, min(n, lo + size)))
+            lo = bounds[-1][1]
         bufs = [torch.empty((chunk_cells, self.G), dtype=torch.int32, device=self.dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=self.dev)
         main = torch.cuda.current_stream(self.dev)
         free = [torch.cuda.Event(), torch.cuda.Event()]
-        for i, lo in enumerate(range(0, n, chunk_cells)):
-            hi = min(n, lo + chunk_cells)
+        for i, (lo, hi) in enumerate(bounds):
             buf = bufs[i & 1][:hi - lo]
             if i >= 2:
                 main.wait_event(free[i & 1])

@@ -14,6 +14,9 @@ Extra keyword-only arguments (never required):
   dtype    dtype of the returned count matrix (reference: int64; int32 avoids a host pass)
   out      "numpy" (reference behaviour) or "torch" (leave everything on the GPU)
   sampler  "gamma_poisson" or "hybrid" 
+  host_out (sample_density) preallocated, ideally pinned, CPU tensors (X int32 (n,G), pseudotime
+           int64, branch codes int32, scalings float64) that receive the result in overlapped
+           chunks: the zero-allocation path for repeated or very large calls
 """
 import warnings
 
@@ -296,19 +299,33 @@ def _finish(engine, tables, X, pt, codes, s64, dtype, out):
 
 
 def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
-                    seed, first, dev, dtype, out, sampler):
-    """Common tail of every sampler (simulation.py:590-599): scalings, then counts."""
+                    seed, first, dev, dtype, out, sampler, host_out=None):
+    """Common tail of every sampler (simulation.py:590-599): scalings, then counts.
+    host_out = (X, pseudotime, branch_codes, scalings) preallocated CPU tensors (int32 (n,G),
+    int64, int32, float64; ideally pinned): the counts are streamed into them in cell chunks
+    while the next chunk is being sampled, and numpy views of them are returned."""
     n = int(rows.numel())
     s64, s32 = sut.calc_scalings(n, scale, scale_mean, scale_v, seed=nat.derive_seed(seed, 1),
                                  first=first, device=dev, return_device=True)
     engine = CountEngine(tree, tables, alpha, beta, dev, sampler=sampler)
+    if host_out is not None:
+        hX, hpt, hcodes, hs = host_out
+        if tuple(hX.shape) != (n, engine.G) or hX.dtype != torch.int32:
+            raise ValueError("host_out[0] must be an int32 CPU tensor of shape (%d, %d)" % (n, engine.G))
+        hpt.copy_(pt, non_blocking=True)
+        hcodes.copy_(codes, non_blocking=True)
+        hs.copy_(s64, non_blocking=True)
+        engine.draw_to_host(rows, s32, nat.derive_seed(seed, 2), first, hX)
+        torch.cuda.current_stream(dev).synchronize()
+        engine.check()
+        return hX.numpy(), hpt.numpy(), tables.branch_names(hcodes.numpy()), hs.numpy()
     X = engine.draw(rows, s32, nat.derive_seed(seed, 2), first)
     return _finish(engine, tables, X, pt, codes, s64, dtype, out)
 
 
 def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, scale_mean=0.,
                    seed=None, device=None, shard=None, dtype=np.int64, out="numpy",
-                   sampler=DEFAULT_SAMPLER, uniforms=None):
+                   sampler=DEFAULT_SAMPLER, uniforms=None, host_out=None):
     """Sample `no_cells` (pseudotime, branch) pairs according to tree.density and draw
     their counts (simulation.py:416-471).  Returns (X, pseudotime, branches, scalings).
     `uniforms` (one per cell) replays externally supplied draws through the index map."""
@@ -330,7 +347,7 @@ def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, s
     nat.call("pst_density_index", nat.ptr(cdf), tables.P, nat.ptr(u), n, nat.ptr(tables.d("pos_pt")),
              nat.ptr(tables.d("pos_branch")), nat.ptr(rows), nat.ptr(pt), nat.ptr(codes), st)
     return _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
-                           seed, lo, dev, dtype, out, sampler)
+                           seed, lo, dev, dtype, out, sampler, host_out=host_out)
 
 
 def cover_whole_tree(tree):

@@ -478,6 +478,14 @@ def test_density_session_equals_api_call():
     host = torch.empty((N, t.G), dtype=torch.int32).pin_memory()
     sess.step_to_host(123, host, chunk_cells=1000)
     assert np.array_equal(host.numpy(), X)
+    # the reference-facing call with preallocated host outputs gives the same bits
+    hX = torch.empty((N, t.G), dtype=torch.int32).pin_memory()
+    hpt, hco, hsc = torch.empty(N, dtype=torch.int64), torch.empty(N, dtype=torch.int32), torch.empty(N, dtype=torch.float64)
+    Xo, pto, bro, sco = sim.sample_density(t, N, alpha=s["alpha"], beta=s["beta"], seed=123, device=DEV,
+                                           sampler="hybrid", host_out=(hX, hpt, hco, hsc))
+    assert np.array_equal(Xo, X) and np.array_equal(pto, pt) and list(bro) == list(br) and np.array_equal(sco, sc)
+    with pytest.raises(ValueError):
+        sim.sample_density(t, N + 1, alpha=s["alpha"], beta=s["beta"], seed=123, device=DEV, host_out=(hX, hpt, hco, hsc))
     # the row-grouped visiting order never changes the counts
     sess.engine.group_rows = False
     sess.step(123)
