@@ -28,6 +28,7 @@ from prosstt_b200 import _native as nat
 from prosstt_b200 import count_model as cm
 from prosstt_b200 import sim_utils as sut
 from prosstt_b200.device import CountEngine, TreeTables, choice_cdf, raise_flags
+from prosstt_b200.sharding import shard_range
 
 DEFAULT_SAMPLER = "hybrid"
 
@@ -283,9 +284,7 @@ def _shard_range(n, shard):
     if shard is None:
         return 0, n
     rank, world = shard
-    if not (0 <= rank < world):
-        raise ValueError("shard must be (rank, world) with 0 <= rank < world")
-    return (n * rank) // world, (n * (rank + 1)) // world
+    return shard_range(n, rank, world)
 
 
 def _finish(engine, tables, X, pt, codes, s64, dtype, out):

@@ -39,15 +39,9 @@ def _worker(rank, world, port, n_cells, seed, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = _shard_range(n_cells, (rank, world))
     local = torch.from_numpy(_global_stream(nat.derive_seed(seed, 0), lo, hi - lo))
-    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([hi - lo]))
-    parts = [torch.zeros(int(s.item()), dtype=torch.float64) for s in sizes]
-    pad = max(int(s.item()) for s in sizes)
-    padded = [torch.zeros(pad, dtype=torch.float64) for _ in range(world)]
-    mine = torch.zeros(pad, dtype=torch.float64)
-    mine[:hi - lo] = local
-    dist.all_gather(padded, mine)
-    full = torch.cat([p[:int(s.item())] for p, s in zip(padded, sizes)])
+    from prosstt_b200.sharding import gather_counts, rank_and_world, shard_range
+    assert rank_and_world() == (rank, world) and shard_range(n_cells, rank, world) == (lo, hi)
+    full = gather_counts(local.reshape(-1, 1), n_cells).reshape(-1)      # the optional gather epilogue
     tmax = torch.tensor([float(rank + 1)])
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)          # the bench's max-over-ranks timing
     if rank == 0:

@@ -14,6 +14,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from prosstt_b200 import simulation as sim  # noqa: E402
+from prosstt_b200.sharding import gather_counts  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -30,16 +31,11 @@ for name, call in (
     ("sample_pseudotime_series", lambda **kw: sim.sample_pseudotime_series(tree, [3000, 2001, 1000], [0, 40, 100], [3.0, 5.0, 8.0], alpha=alpha, beta=beta, seed=7, device=dev, out="torch", **kw)),
 ):
     X, pt, codes, sc = call(shard=(rank, world))
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([X.shape[0]], device=dev))
-    pad = int(max(s.item() for s in sizes))
-    mine = torch.zeros((pad, X.shape[1]), dtype=torch.int32, device=dev)
-    mine[:X.shape[0]] = X
-    slabs = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(slabs, mine)                               # NCCL over NVLink
+    total = torch.tensor([X.shape[0]], device=dev)
+    dist.all_reduce(total)
+    gathered = gather_counts(X, int(total.item()))               # NCCL over NVLink
     if rank == 0:
         whole = call()[0]
-        gathered = torch.cat([s[:int(n.item())] for s, n in zip(slabs, sizes)])
         same = torch.equal(gathered, whole)
         ok &= same
         print("%-26s world=%d cells=%d genes=%d  gathered shards == single-GPU result: %s  (sum %d)"
