@@ -291,10 +291,26 @@ def _finish(engine, tables, X, pt, codes, s64, dtype, out):
     engine.check()
     if out == "torch":
         return X, pt, codes, s64
-    Xh = X.cpu().numpy()
-    if np.dtype(dtype) != Xh.dtype:
-        Xh = Xh.astype(dtype)
-    return Xh, pt.cpu().numpy(), tables.branch_names(codes.cpu().numpy()), s64.cpu().numpy()
+    return _counts_to_host(X, dtype), pt.cpu().numpy(), tables.branch_names(codes.cpu().numpy()), s64.cpu().numpy()
+
+
+_TORCH_INT = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.int16): torch.int16,
+              np.dtype(np.uint8): torch.uint8, np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
+
+
+def _counts_to_host(X, dtype):
+    """Device int32 counts -> host ndarray of `dtype` (reference: int64).  The widening is done on
+    the device chunk by chunk, so the host never runs an astype pass over the matrix."""
+    want = np.dtype(dtype)
+    if want == np.dtype(np.int32) or want not in _TORCH_INT:
+        Xh = X.cpu().numpy()
+        return Xh if want == Xh.dtype else Xh.astype(want)
+    n, G = X.shape
+    host = torch.empty((n, G), dtype=_TORCH_INT[want])
+    step = max(1, (256 << 20) // max(1, 8 * G))
+    for lo in range(0, n, step):
+        host[lo:lo + step].copy_(X[lo:lo + step].to(_TORCH_INT[want]))
+    return host.numpy()
 
 
 def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
@@ -497,8 +513,7 @@ def draw_counts(tree, pseudotime, branches, scalings, alpha, beta, seed=None, de
     engine.check()
     if out == "torch":
         return X
-    Xh = X.cpu().numpy()
-    return Xh if np.dtype(dtype) == Xh.dtype else Xh.astype(dtype)
+    return _counts_to_host(X, dtype)
 
 
 def add_non_diff_genes(inform_expr_matrix, genes, gene_params, cell_scalings, seed=None,
