@@ -156,6 +156,96 @@ __device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, uint32_t 
   return nb_gamma_poisson_draw(mu, theta, rng);
 }
 
+// ---------------------------------------------------------------------------
+// Mixture draw as a restartable state machine (hybrid kernel).  One call = one Marsaglia-Tsang
+// attempt (if lambda is not known yet) + up to two PTRS trials, all from two Philox blocks; a
+// rejected entry goes back to the queue and is retried with the next block, so a warp never
+// spins in a rejection loop while 31 lanes wait.
+//   blocks of the per-(cell,gene) stream: 2a   -> gamma attempt a (normal, accept, boost)
+//                                          2a+1 -> Poisson attempt a (two PTRS trials / inversion)
+// ---------------------------------------------------------------------------
+enum : int { MIX_DONE = 0, MIX_RETRY_GAMMA = 1, MIX_RETRY_POISSON = 2 };
+struct MixResult { float value; int status; };   // value: count (DONE) or lambda (RETRY_POISSON)
+
+__device__ __forceinline__ bool ptrs_trial(float lam, float loglam, float a, float b, float inv_alpha,
+                                           float vr, float U, float V, float &k) {
+  const float us = 0.5f - fabsf(U);
+  k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+  if (us >= 0.07f && V <= vr) return true;
+  if (k < 0.f || (us < 0.013f && V > us)) return false;
+  float bound;
+  if (k < 16.f) {
+    bound = -lam + k * loglam - c_logfact[(int)k];
+  } else {
+    const float y = (lam - k) / k;
+    const float ik = 1.0f / k;
+    bound = k * (log1pf(y) - y) - 0.5f * __logf(6.2831853072f * k) -
+            ik * (0.0833333333f - 0.0027777778f * ik * ik);
+  }
+  return __logf(V) + __logf(inv_alpha) - __logf(a / (us * us) + b) <= bound;
+}
+
+__device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_lambda, int attempt,
+                                               uint32_t key0, uint32_t key1, uint32_t gene, int64_t cell) {
+  const uint32_t c1 = (uint32_t)cell, c2 = (TAG_COUNT << 16) | (uint32_t)((uint64_t)cell >> 32);
+  const bool force = attempt >= 62;               // never reached in practice (p ~ 0.1^62)
+  float lam;
+  int pa = attempt;                                // Poisson attempt index
+  if (!have_lambda) {                              // x = mu: gamma stage
+    const float mu = x;
+    const float r = mu / theta;
+    const bool lt1 = r < 1.0f;
+    const float shape = lt1 ? r + 1.0f : r;
+    const uint4 w = philox_s(key0, key1, gene, c1, c2, 2u * (uint32_t)attempt);
+    const float d = shape - 0.3333333333f;
+    const float c = rsqrtf(9.0f * d);
+    const float xn = sqrtf(-2.0f * __logf(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
+    const float e = c * xn;
+    const float t = 1.0f + e;
+    const float v = t * t * t;
+    const float u = u01(w.z);
+    const float x2 = xn * xn;
+    bool ok = t > 0.f;
+    if (ok && !(u < 1.0f - 0.0331f * x2 * x2)) {
+      float h;
+      if (fabsf(e) < 0.1f) {
+        const float e2 = e * e;
+        h = d * e2 * e2 * (-0.75f + e * (0.6f + e * (-0.5f + e * (0.4285714286f + e * (-0.375f + e * 0.3333333333f)))));
+      } else {
+        h = 0.5f * x2 + d * (1.0f - v + __logf(v));
+      }
+      ok = __logf(u) < h;
+    }
+    if (!ok && !force) return MixResult{0.f, MIX_RETRY_GAMMA};
+    const float boost = lt1 ? __expf(__fdividef(__logf(u01(w.w)), r)) : 1.0f;   // Gamma(r) = Gamma(r+1) U^(1/r)
+    lam = theta * d * fmaxf(v, 0.f) * boost;
+    pa = 0;
+  } else {
+    lam = x;                                       // gamma already accepted
+  }
+  const uint4 w = philox_s(key0, key1, gene, c1, c2, 2u * (uint32_t)pa + 1u);
+  float k;
+  if (lam < 10.f) {                                // inversion, one uniform
+    const float u = u01(w.x);
+    float p = __expf(-lam), cdf = p;
+    k = 0.f;
+    while (u > cdf && k < 96.f) { k += 1.0f; p *= __fdividef(lam, k); cdf += p; }
+  } else if (lam < 1.6e7f) {                       // PTRS (Hoermann 1993), two trials per block
+    const float slam = sqrtf(lam), loglam = __logf(lam);
+    const float b = 0.931f + 2.53f * slam;
+    const float a = -0.059f + 0.02483f * b;
+    const float inv_alpha = 1.1239f + 1.1328f / (b - 3.4f);
+    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    bool ok = ptrs_trial(lam, loglam, a, b, inv_alpha, vr, u01(w.x) - 0.5f, u01(w.y), k);
+    if (!ok) ok = ptrs_trial(lam, loglam, a, b, inv_alpha, vr, u01(w.z) - 0.5f, u01(w.w), k);
+    if (!ok && !force) return MixResult{lam, MIX_RETRY_POISSON};
+    k = fmaxf(k, 0.f);
+  } else {                                         // beyond 2^24: normal limit (TV error < 1e-4)
+    k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * __logf(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));
+  }
+  return MixResult{k, MIX_DONE};
+}
+
 __device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
   return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
 }
@@ -206,8 +296,7 @@ draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ me
         if (VEC || g0 + j < G) {
           const float mu = m[j] * s, theta = fmaf(a[j], mu, b[j]);
           if (!nb_domain_ok(mu, theta)) { flag |= PST_FLAG_DOMAIN; continue; }
-          GeneStream rng(key0, key1, (uint32_t)(g0 + j), cell0 + cell);
-          out[j] = nb_gamma_poisson_draw(mu, theta, rng);
+          out[j] = nb_gamma_poisson_mt(mu, theta, key0, key1, (uint32_t)(g0 + j), cell0 + cell);
           if (out[j] == 2147483647) flag |= PST_FLAG_CLAMPED;
         }
       }
@@ -259,7 +348,8 @@ static_assert(HY_MU_MAX <= 32.0f && HY_KFIX >= 10, "frozen-cdf guard needs P(k>=
 struct HyWarpQueues {
   float4 se[HY_QCAP];       // inversion tail: P(k), cdf(k)-u, a, q
   int2 sw[HY_QCAP];         //                 where the count goes: (cell, gene)
-  float4 ge[HY_QCAP];       // mixture: mu, theta, cell, gene (ints bit-cast)
+  float4 ge[HY_QCAP];       // mixture: mu (or lambda once the gamma is accepted), theta, cell, gene
+  int ga[HY_QCAP];          //          attempt counter of the current stage | stage << 16
   float4 mstage[32];        // next cell's means quad, filled by cp.async (one slot per lane)
 };
 
@@ -270,7 +360,7 @@ struct HyWarpQueues {
                             1.0f / 20922789888000.0f}
 
 #ifndef HY_MIN_CTAS
-#define HY_MIN_CTAS 8
+#define HY_MIN_CTAS 7     // 28 warps/SM: 72 registers and 28.9 KB of queues per CTA
 #endif
 constexpr int HY_CHUNK_CELLS = 64;           // cells per chunk (x 32 quads = 8192 counts)
 
@@ -332,19 +422,44 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       X[(int64_t)w.x * ldx + w.y] = cn;
     }
   };
-  auto drain_mixture = [&](int first, int cnt) {
-    if (lane < cnt) {
-      const float4 g = wq.ge[first + lane];
-      const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w);
-      int val = 0;
-      if (nb_domain_ok(g.x, g.y)) {
-        val = nb_gamma_poisson_mt(g.x, g.y, key0, key1, (uint32_t)gene, cell0 + ccell);
-        if (val == 2147483647) flag |= PST_FLAG_CLAMPED;
+  // one mixture step for up to 32 queued entries; rejected entries go back to the queue (returns
+  // how many), so the warp never spins in a rejection loop
+  auto drain_mixture = [&](int first, int cnt) -> int {
+    const bool act = lane < cnt;
+    float4 g = make_float4(1.f, 1.f, 0.f, 0.f);
+    int ga = 0;                                     // attempt | stage << 16 (stage 1: x holds lambda)
+    if (act) { g = wq.ge[first + lane]; ga = wq.ga[first + lane]; }
+    __syncwarp();                                   // every entry is read before slots are reused
+    const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w);
+    const bool have_lambda = (ga >> 16) != 0;
+    const int att = ga & 0xffff;
+    int status = MIX_DONE;
+    float value = 0.f;
+    if (act) {
+      if (!have_lambda && !nb_domain_ok(g.x, g.y)) {
+        flag |= PST_FLAG_DOMAIN;                    // count stays 0
       } else {
-        flag |= PST_FLAG_DOMAIN;
+        const MixResult res = mixture_step(g.x, g.y, have_lambda, att, key0, key1, (uint32_t)gene, cell0 + ccell);
+        status = res.status;
+        value = res.value;
       }
-      X[(int64_t)ccell * ldx + gene] = val;
+      if (status == MIX_DONE) {
+        int val = (int)value;
+        if (value > 2147483520.f) { val = 2147483647; flag |= PST_FLAG_CLAMPED; }
+        X[(int64_t)ccell * ldx + gene] = val;
+      }
     }
+    const bool again = act && status != MIX_DONE;
+    const unsigned m = __ballot_sync(0xffffffffu, again);
+    if (again) {
+      const int e = first + __popc(m & lt_mask);
+      // a rejected gamma keeps (mu, theta); an accepted gamma with rejected Poisson trials keeps
+      // lambda (stage 1); either way the next attempt of that stage uses the next Philox block
+      wq.ge[e] = (status == MIX_RETRY_GAMMA) ? g : make_float4(value, g.y, g.z, g.w);
+      wq.ga[e] = (status == MIX_RETRY_GAMMA) ? att + 1 : ((1 << 16) | (have_lambda ? att + 1 : 1));
+    }
+    __syncwarp();
+    return __popc(m);
   };
 
   // Work decomposition: a chunk is a strip of 32 gene quads (one per lane, 128 genes = 512
@@ -469,6 +584,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         if (to_mix) {
           const int e = ng + __popc(mg & lt_mask);
           wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
+          wq.ga[e] = 0;
         }
         ng += __popc(mg);
       }
@@ -520,7 +636,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       }
       __syncwarp();
       while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
-      while (ng >= 32) { ng -= 32; drain_mixture(ng, 32); }
+      while (ng >= 32) { ng -= 32; ng += drain_mixture(ng, 32); }
       __syncwarp();
       // rotate the pipeline
       if (VEC) {
@@ -531,7 +647,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     }
   }
   if (ns > 0) drain_search(0, ns);
-  if (ng > 0) drain_mixture(0, ng);
+  while (ng > 0) { const int c = ng < 32 ? ng : 32; ng -= c; ng += drain_mixture(ng, c); }
   if (flag) atomicOr(flags, flag);
   // the last warp to leave rearms the scheduler words for the next launch
   if (lane == 0) {

@@ -19,6 +19,7 @@ ap.add_argument("--cells", type=int, default=200000)
 ap.add_argument("--genes", type=int, default=20000)
 ap.add_argument("--samplers", default="gamma_poisson,hybrid")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--scale-mean", type=float, default=0.0, help="mean of log library size (depth regime)")
 a = ap.parse_args()
 args = argparse.Namespace(branch_points=7, steps_per_branch=50, programs=10, genes=a.genes, cells=a.cells)
 dev = torch.device("cuda", 0)
@@ -28,7 +29,7 @@ tree = bench.build_tree_gpu(args, dev)
 alpha, beta = bench.gene_hyper(a.genes)
 print("tree built in %.1fs" % (time.time() - t0), flush=True)
 for name in a.samplers.split(","):
-    s = DensitySession(tree, alpha, beta, a.cells, device=dev, sampler=name)
+    s = DensitySession(tree, alpha, beta, a.cells, device=dev, sampler=name, scale_mean=a.scale_mean)
     s.step(1)
     torch.cuda.synchronize()
     ms = []
