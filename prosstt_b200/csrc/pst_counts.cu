@@ -323,13 +323,16 @@ draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ me
 //   (d += t/k!, 1/k! an immediate) and one integer op adding the sign bit of d to the count.
 //   The four uniforms of a thread come from ONE Philox block keyed (cell, gene quad).
 //   Tail: counts still undecided after KFIX terms (u above the cdf) are pushed to a per-warp
-//   shared-memory queue and finished 32 at a time with k warp-uniform (1/(k+1) from a
-//   constant table), so the tail runs at full warp width whatever the mix of means.
+//   shared-memory queue and finished 32 at a time with k warp-uniform (HY_STAGE2 more unrolled
+//   terms, then a generic loop with a vote every 4 terms), so the tail runs at full warp width
+//   whatever the mix of means.
 // Large means are pushed to a second per-warp queue and drawn 32 at a time by the mixture
-//   (Marsaglia-Tsang + PTRS) on their own per-(cell, gene) Philox stream.
+//   (Marsaglia-Tsang + PTRS) on their own per-(cell, gene) Philox stream; the draw is a
+//   restartable step (mixture_step): rejected entries are re-queued, no warp spins in a loop.
 // The head writes the quad with one 128-bit store (0 in undecided slots); queue results are
 //   written with 4-byte stores after a __syncwarp (same warp, ordered).
 // The route depends on the parameters only, never on the uniforms, so the draw is unbiased.
+// Work decomposition, prefetching and the dynamic chunk scheduler are described at the loop.
 // ---------------------------------------------------------------------------
 constexpr int HY_WARPS = 4;                  // warps per CTA
 constexpr int HY_THREADS = HY_WARPS * 32;
