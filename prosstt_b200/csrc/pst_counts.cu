@@ -13,148 +13,25 @@
 // (seed, cell, gene or gene quad, draw index) through Philox4x32-10, so counts do not depend
 // on launch shape, cell partition or GPU count.
 //
-// Two samplers (both exact up to fp32 rounding, see DESIGN.md "sampler accuracy"):
-//   PST_SAMPLER_GAMMA_POISSON  the mixture exactly as numpy draws it: Marsaglia-Tsang gamma,
-//                              then Poisson by PTRS (lam >= 10) or inversion (lam < 10)
-//   PST_SAMPLER_HYBRID         direct inversion of the NB cdf with ONE uniform for small
-//                              means (branch-free unrolled head + compacted tail), the
-//                              mixture above for large means, both queue-compacted per warp
+// Two samplers (both exact up to fp32 rounding, see DESIGN.md "sampler accuracy"), one kernel:
+//   PST_SAMPLER_GAMMA_POISSON  every count by the mixture the way NumPy's legacy generator draws
+//                              it: Marsaglia-Tsang gamma, then Poisson by PTRS (lam >= 10) or
+//                              inversion (lam < 10)
+//   PST_SAMPLER_HYBRID         direct inversion of the NB cdf with ONE uniform for small means
+//                              (branch-free unrolled head + compacted tail), the mixture for
+//                              large means
+// In both, work that would make a warp diverge is pushed to per-warp shared-memory queues and
+// executed 32 entries at a time.
 #include <stdlib.h>
 #include <algorithm>
 #include "pst_common.cuh"
 
 namespace pst {
 
-// ---------------------------------------------------------------------------
-// per-(cell,gene) word stream for the mixture path
-// ---------------------------------------------------------------------------
-struct GeneStream {
-  uint32_t k0, k1, c0, c1, c2, blk;
-  uint4 buf;
-  int left;
-  __device__ GeneStream(uint32_t key0, uint32_t key1, uint32_t gene, int64_t cell)
-      : k0(key0), k1(key1), c0(gene), c1((uint32_t)cell),
-        c2((TAG_COUNT << 16) | (uint32_t)((uint64_t)cell >> 32)), blk(0), left(0) {}
-  __device__ __forceinline__ uint32_t next() {
-    if (left == 0) { buf = philox_s(k0, k1, c0, c1, c2, blk++); left = 4; }
-    const uint32_t w = buf.x;
-    buf.x = buf.y; buf.y = buf.z; buf.z = buf.w;
-    --left;
-    return w;
-  }
-  __device__ __forceinline__ float uniform() { return u01(next()); }
-};
-
 __constant__ float c_logfact[16] = {0.f, 0.f, 0.6931471806f, 1.7917594692f, 3.1780538303f,
                                     4.7874917428f, 6.5792512120f, 8.5251613611f, 10.6046029027f,
                                     12.8018274801f, 15.1044125730f, 17.5023078459f, 19.9872144957f,
                                     22.5521638531f, 25.1912211827f, 27.8992713838f};
-
-// Poisson(lam), lam >= 10: PTRS transformed rejection (Hoermann 1993), the algorithm numpy's
-// legacy generator uses for lam >= 10.  The acceptance bound -lam + k log(lam) - log(k!) is
-// evaluated as k(log1p(y)-y) - log(sqrt(2 pi k)) - 1/(12k)+..., y = (lam-k)/k, which stays
-// accurate in fp32 for lam up to 2^24.
-__device__ __forceinline__ float poisson_ptrs(float lam, GeneStream &rng) {
-  const float slam = sqrtf(lam);
-  const float loglam = __logf(lam);
-  const float b = 0.931f + 2.53f * slam;
-  const float a = -0.059f + 0.02483f * b;
-  const float inv_alpha = 1.1239f + 1.1328f / (b - 3.4f);
-  const float vr = 0.9277f - 3.6224f / (b - 2.0f);
-  float k = 0.f;
-  for (int it = 0; it < 64; ++it) {
-    const float U = rng.uniform() - 0.5f;
-    const float V = rng.uniform();
-    const float us = 0.5f - fabsf(U);
-    k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
-    if (us >= 0.07f && V <= vr) break;
-    if (k < 0.f || (us < 0.013f && V > us)) continue;
-    float bound;
-    if (k < 16.f) {
-      bound = -lam + k * loglam - c_logfact[(int)k];
-    } else {
-      const float y = (lam - k) / k;
-      const float ik = 1.0f / k;
-      bound = k * (log1pf(y) - y) - 0.5f * __logf(6.2831853072f * k) -
-              ik * (0.0833333333f - 0.0027777778f * ik * ik);
-    }
-    if (__logf(V) + __logf(inv_alpha) - __logf(a / (us * us) + b) <= bound) break;
-  }
-  return k;
-}
-
-// Poisson(lam), lam < 10: sequential inversion with one uniform
-__device__ __forceinline__ float poisson_small(float lam, GeneStream &rng) {
-  const float u = rng.uniform();
-  float p = __expf(-lam), cdf = p, k = 0.f;
-  while (u > cdf && k < 96.f) {
-    k += 1.0f;
-    p *= __fdividef(lam, k);
-    cdf += p;
-  }
-  return k;
-}
-
-// standard gamma, shape a >= 1, by Marsaglia-Tsang (2000); returns d*v
-__device__ __forceinline__ float gamma_mt(float a, GeneStream &rng) {
-  const float d = a - 0.3333333333f;
-  const float c = rsqrtf(9.0f * d);
-  float v = 1.0f;
-  for (int it = 0; it < 64; ++it) {
-    // Box-Muller (cosine branch)
-    const float u1 = rng.uniform(), u2 = rng.uniform();
-    const float x = sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853072f * u2 - 3.1415926536f);
-    const float e = c * x;
-    const float t = 1.0f + e;
-    if (t <= 0.f) continue;
-    v = t * t * t;
-    const float u = rng.uniform();
-    const float x2 = x * x;
-    if (u < 1.0f - 0.0331f * x2 * x2) break;
-    // log u < x^2/2 + d(1 - v + log v); for small |e| the right side is the series
-    // d e^4 (-3/4 + 3/5 e - 1/2 e^2 + 3/7 e^3 - 3/8 e^4 ...) (cancellation-free)
-    float h;
-    if (fabsf(e) < 0.1f) {
-      const float e2 = e * e;
-      h = d * e2 * e2 * (-0.75f + e * (0.6f + e * (-0.5f + e * (0.4285714286f + e * (-0.375f + e * 0.3333333333f)))));
-    } else {
-      h = 0.5f * x2 + d * (1.0f - v + __logf(v));
-    }
-    if (__logf(u) < h) break;
-  }
-  return d * v;
-}
-
-// gamma-Poisson draw for valid (mu, theta): lambda = theta * Gamma(mu/theta), X ~ Poisson(lambda)
-// (returns INT32_MAX when the count does not fit: the caller raises PST_FLAG_CLAMPED)
-__device__ __forceinline__ int nb_gamma_poisson_draw(float mu, float theta, GeneStream &rng) {
-  const float r = mu / theta;
-  float g;
-  if (r >= 1.0f) {
-    g = gamma_mt(r, rng);
-  } else {
-    // Gamma(r) = Gamma(r+1) * U^(1/r)
-    const float u = rng.uniform();
-    g = gamma_mt(r + 1.0f, rng) * __expf(__fdividef(__logf(u), r));
-  }
-  const float lam = theta * g;
-  float k;
-  if (lam < 10.f) k = poisson_small(lam, rng);
-  else if (lam < 1.6e7f) k = poisson_ptrs(lam, rng);
-  else {
-    // beyond 2^24 a float cannot hold every integer: normal limit (TV error < 1e-4)
-    const float u1 = rng.uniform(), u2 = rng.uniform();
-    k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853072f * u2 - 3.1415926536f));
-  }
-  return (k > 2147483520.f) ? 2147483647 : (int)k;
-}
-
-// out-of-line entry for the hybrid kernel's queue (keeps the head's register budget small)
-__device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, uint32_t key0, uint32_t key1,
-                                                uint32_t gene, int64_t cell) {
-  GeneStream rng(key0, key1, gene, cell);
-  return nb_gamma_poisson_draw(mu, theta, rng);
-}
 
 // ---------------------------------------------------------------------------
 // Mixture draw as a restartable state machine (hybrid kernel).  One call = one Marsaglia-Tsang
@@ -167,22 +44,35 @@ __device__ __noinline__ int nb_gamma_poisson_mt(float mu, float theta, uint32_t 
 enum : int { MIX_DONE = 0, MIX_RETRY_GAMMA = 1, MIX_RETRY_POISSON = 2 };
 struct MixResult { float value; int status; };   // value: count (DONE) or lambda (RETRY_POISSON)
 
-__device__ __forceinline__ bool ptrs_trial(float lam, float loglam, float a, float b, float inv_alpha,
+// Poisson(lam), lam >= 10: one trial of PTRS (Hoermann 1993, the transformed-rejection sampler
+// NumPy's legacy generator uses for lam >= 10).  The acceptance bound -lam + k log(lam) - log(k!)
+// is evaluated as k(log1p(y) - y) - log(sqrt(2 pi k)) - 1/(12k) + 1/(360k^3), y = (lam-k)/k,
+// which stays accurate in fp32 up to lam = 2^24.
+__device__ __forceinline__ bool ptrs_trial(float lam, float loglam, float a, float b, float log_inv_alpha,
                                            float vr, float U, float V, float &k) {
   const float us = 0.5f - fabsf(U);
-  k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+  const float ius = rcp_fast(us);
+  k = floorf(fmaf(fmaf(2.0f * a, ius, b), U, lam + 0.43f));
   if (us >= 0.07f && V <= vr) return true;
   if (k < 0.f || (us < 0.013f && V > us)) return false;
   float bound;
   if (k < 16.f) {
     bound = -lam + k * loglam - c_logfact[(int)k];
   } else {
-    const float y = (lam - k) / k;
-    const float ik = 1.0f / k;
-    bound = k * (log1pf(y) - y) - 0.5f * __logf(6.2831853072f * k) -
-            ik * (0.0833333333f - 0.0027777778f * ik * ik);
+    const float ik = rcp_fast(k);
+    const float y = (lam - k) * ik;
+    // log1p(y) - y without cancellation: series for |y| < 1/4, log1pf beyond
+    float l1;
+    if (fabsf(y) < 0.25f) {
+      const float y2 = y * y;
+      l1 = y2 * (-0.5f + y * (0.3333333333f + y * (-0.25f + y * (0.2f + y * (-0.1666666667f + y * (0.1428571429f +
+           y * (-0.125f + y * (0.1111111111f + y * (-0.1f + y * 0.0909090909f)))))))));
+    } else {
+      l1 = log1pf(y) - y;
+    }
+    bound = k * l1 - 0.5f * __logf(6.2831853072f * k) - ik * (0.0833333333f - 0.0027777778f * ik * ik);
   }
-  return __logf(V) + __logf(inv_alpha) - __logf(a / (us * us) + b) <= bound;
+  return __logf(V) + log_inv_alpha - __logf(fmaf(a * ius, ius, b)) <= bound;
 }
 
 __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_lambda, int attempt,
@@ -193,13 +83,14 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   int pa = attempt;                                // Poisson attempt index
   if (!have_lambda) {                              // x = mu: gamma stage
     const float mu = x;
-    const float r = mu / theta;
+    const float r = __fdividef(mu, theta);
     const bool lt1 = r < 1.0f;
     const float shape = lt1 ? r + 1.0f : r;
     const uint4 w = philox_s(key0, key1, gene, c1, c2, 2u * (uint32_t)attempt);
     const float d = shape - 0.3333333333f;
     const float c = rsqrtf(9.0f * d);
-    const float xn = sqrtf(-2.0f * __logf(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
+    const float rad2 = -2.0f * __logf(u01(w.x));                    // Box-Muller, cosine branch
+    const float xn = rad2 * rsqrtf(fmaxf(rad2, 1e-30f)) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
     const float e = c * xn;
     const float t = 1.0f + e;
     const float v = t * t * t;
@@ -231,85 +122,23 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
     k = 0.f;
     while (u > cdf && k < 96.f) { k += 1.0f; p *= __fdividef(lam, k); cdf += p; }
   } else if (lam < 1.6e7f) {                       // PTRS (Hoermann 1993), two trials per block
-    const float slam = sqrtf(lam), loglam = __logf(lam);
-    const float b = 0.931f + 2.53f * slam;
-    const float a = -0.059f + 0.02483f * b;
-    const float inv_alpha = 1.1239f + 1.1328f / (b - 3.4f);
-    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
-    bool ok = ptrs_trial(lam, loglam, a, b, inv_alpha, vr, u01(w.x) - 0.5f, u01(w.y), k);
-    if (!ok) ok = ptrs_trial(lam, loglam, a, b, inv_alpha, vr, u01(w.z) - 0.5f, u01(w.w), k);
+    const float slam = lam * rsqrtf(lam), loglam = __logf(lam);
+    const float b = fmaf(2.53f, slam, 0.931f);
+    const float a = fmaf(0.02483f, b, -0.059f);
+    const float log_inv_alpha = __logf(1.1239f + __fdividef(1.1328f, b - 3.4f));
+    const float vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
+    bool ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.x) - 0.5f, u01(w.y), k);
+    if (!ok) ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.z) - 0.5f, u01(w.w), k);
     if (!ok && !force) return MixResult{lam, MIX_RETRY_POISSON};
     k = fmaxf(k, 0.f);
   } else {                                         // beyond 2^24: normal limit (TV error < 1e-4)
-    k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * __logf(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));
+    k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * __logf(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));   // never hot
   }
   return MixResult{k, MIX_DONE};
 }
 
 __device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
   return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
-}
-
-// ---------------------------------------------------------------------------
-// kernel "gamma_poisson": the mixture for every count
-// ---------------------------------------------------------------------------
-constexpr int DC_THREADS = 256;
-
-template <bool VEC>
-__global__ void __launch_bounds__(DC_THREADS)
-draw_counts_gp_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ means, int64_t P, int64_t G,
-                      int64_t Q, const int32_t *__restrict__ row_of_cell,
-                      const float *__restrict__ scaling, const float *__restrict__ alpha,
-                      const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
-                      int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags) {
-  const int64_t items = n * Q;
-  const int64_t stride = (int64_t)gridDim.x * DC_THREADS;
-  uint32_t flag = 0;
-  for (int64_t it = (int64_t)blockIdx.x * DC_THREADS + threadIdx.x; it < items; it += stride) {
-    const int64_t cell = it / Q;
-    const int64_t g0 = (it - cell * Q) * 4;
-    const int32_t row = row_of_cell[cell];
-    int out[4] = {0, 0, 0, 0};
-    if (row < 0 || row >= P) {
-      flag |= PST_FLAG_ROW;
-    } else {
-      const float s = scaling[cell];
-      float m[4], a[4], b[4];
-      if (VEC) {
-        const float4 mv = *reinterpret_cast<const float4 *>(means + (int64_t)row * G + g0);
-        const float4 av = *reinterpret_cast<const float4 *>(alpha + g0);
-        const float4 bv = *reinterpret_cast<const float4 *>(beta_m1 + g0);
-        m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
-        b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool ok = g0 + j < G;
-          m[j] = ok ? means[(int64_t)row * G + g0 + j] : 1.f;
-          a[j] = ok ? alpha[g0 + j] : 0.f;
-          b[j] = ok ? beta_m1[g0 + j] : 1.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (VEC || g0 + j < G) {
-          const float mu = m[j] * s, theta = fmaf(a[j], mu, b[j]);
-          if (!nb_domain_ok(mu, theta)) { flag |= PST_FLAG_DOMAIN; continue; }
-          out[j] = nb_gamma_poisson_mt(mu, theta, key0, key1, (uint32_t)(g0 + j), cell0 + cell);
-          if (out[j] == 2147483647) flag |= PST_FLAG_CLAMPED;
-        }
-      }
-    }
-    if (VEC) {
-      __stcs(reinterpret_cast<int4 *>(X + cell * ldx + g0), make_int4(out[0], out[1], out[2], out[3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (g0 + j < G) X[cell * ldx + g0 + j] = out[j];
-    }
-  }
-  if (flag) atomicOr(flags, flag);
 }
 
 // ---------------------------------------------------------------------------
@@ -367,7 +196,7 @@ struct HyWarpQueues {
 #endif
 constexpr int HY_CHUNK_CELLS = 64;           // cells per chunk (x 32 quads = 8192 counts)
 
-template <int KFIX, bool VEC>
+template <int KFIX, bool VEC, bool ALL_MIX>
 __global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
 draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, int64_t P,
                           int64_t G, uint32_t Q, const int32_t *__restrict__ row_of_cell,
@@ -550,13 +379,22 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       if (!row_ok) flag |= PST_FLAG_ROW;
       const bool live = lane_ok && row_ok;
       const float m[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
+      float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
+      int cnt[4];
+      bool small[4];
+      if constexpr (ALL_MIX) {
+        // "gamma_poisson" sampler: every count is drawn by the mixture (through the same queue)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mu[j] = m[j] * s;
+          th[j] = fmaf(al[j], mu[j], bm[j]);
+          small[j] = false; t[j] = 0.f; d[j] = 0.f; a[j] = 0.f; q[j] = 0.f; e2[j] = 0.f; cnt[j] = 0;
+        }
+      } else {
       const int64_t gcell = cell0 + cell;
       const uint4 rnd = philox(key, quad, (uint32_t)gcell,
                                (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
       const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-      float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
-      int cnt[4];
-      bool small[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         mu[j] = m[j] * s;
@@ -579,6 +417,14 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
           e2[j] = (x < 0.1f) ? -1.4426950409f * mu[j] * ser : e2[j];
         }
       }
+      // P(0) and cdf(0) - u for the inversion lanes
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[j] = ex2_fast(e2[j]);                     // P(0)
+        d[j] = t[j] - u01(rw[j]);                   // cdf(0) - u
+        cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
+      }
+      }  // !ALL_MIX
       // large means: queue them for the mixture now, so mu/theta are dead during the head
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -591,13 +437,8 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         }
         ng += __popc(mg);
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[j] = ex2_fast(e2[j]);                     // P(0)
-        d[j] = t[j] - u01(rw[j]);                   // cdf(0) - u
-        cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
-      }
       // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
+      if constexpr (!ALL_MIX) {
 #pragma unroll
       for (int k = 0; k < KFIX - 1; ++k) {
 #pragma unroll
@@ -607,6 +448,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
           cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
         }
       }
+      }  // !ALL_MIX
       bool to_search[4];
       int out[4];
 #pragma unroll
@@ -740,10 +582,8 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)means % 16 == 0) &&
                    ((uintptr_t)alpha % 16 == 0) && ((uintptr_t)beta_m1 % 16 == 0) &&
                    ((uintptr_t)X % 16 == 0);
-  const int64_t items = n * Q;
-  const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sampler == PST_SAMPLER_HYBRID) {
+  {
     // The route thresholds and the head length are part of the sampler's definition (they decide
     // which uniforms a count consumes).  A developer build (-DPST_DEV_KNOBS, tools/tune_hybrid.sh)
     // can override them from the environment for profiling sweeps; the product build cannot.
@@ -762,37 +602,31 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
     const int64_t need = (n_chunks + HY_WARPS - 1) / HY_WARPS;
     const int64_t cap = (int64_t)kNumSM * ctas_per_sm;    // persistent CTAs of 4 warps, one wave
     const unsigned hb = (unsigned)(need < cap ? need : cap);
-#define PST_LAUNCH_HYBRID(KF)                                                                              \
+#define PST_LAUNCH_HYBRID(KF, MIX)                                                                         \
     do {                                                                                                   \
-      if (vec) draw_counts_hybrid_kernel<KF, true><<<hb, HY_THREADS, 0, st>>>(                             \
+      if (vec) draw_counts_hybrid_kernel<KF, true, MIX><<<hb, HY_THREADS, 0, st>>>(                        \
           PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
           ldx, flags, cell_order, mu_max, var_max);                                                        \
-      else draw_counts_hybrid_kernel<KF, false><<<hb, HY_THREADS, 0, st>>>(                                \
+      else draw_counts_hybrid_kernel<KF, false, MIX><<<hb, HY_THREADS, 0, st>>>(                           \
           PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
           ldx, flags, cell_order, mu_max, var_max);                                                        \
     } while (0)
+    if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
+      PST_LAUNCH_HYBRID(HY_KFIX, true);
+      return check_launch(fn);
+    }
 #ifdef PST_DEV_KNOBS
     switch (kfix) {
-      case 6: PST_LAUNCH_HYBRID(6); break;
-      case 8: PST_LAUNCH_HYBRID(8); break;
-      case 12: PST_LAUNCH_HYBRID(12); break;
-      default: PST_LAUNCH_HYBRID(HY_KFIX); break;
+      case 6: PST_LAUNCH_HYBRID(6, false); break;
+      case 8: PST_LAUNCH_HYBRID(8, false); break;
+      case 12: PST_LAUNCH_HYBRID(12, false); break;
+      default: PST_LAUNCH_HYBRID(HY_KFIX, false); break;
     }
 #else
     (void)kfix;
-    PST_LAUNCH_HYBRID(HY_KFIX);
+    PST_LAUNCH_HYBRID(HY_KFIX, false);
 #endif
 #undef PST_LAUNCH_HYBRID
     return check_launch(fn);
   }
-  int64_t blocks = (items + DC_THREADS - 1) / DC_THREADS;
-  const int64_t cap = (int64_t)kNumSM * 8 * 4;            // 4 waves of 8 CTAs per SM, then grid-stride
-  if (blocks > cap) blocks = cap;
-  if (vec)
-    draw_counts_gp_kernel<true><<<(unsigned)blocks, DC_THREADS, 0, st>>>(
-        key0, key1, means, P, G, Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
-  else
-    draw_counts_gp_kernel<false><<<(unsigned)blocks, DC_THREADS, 0, st>>>(
-        key0, key1, means, P, G, Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X, ldx, flags);
-  return check_launch(fn);
 }
