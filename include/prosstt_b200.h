@@ -181,6 +181,16 @@ int pst_draw_counts(const float *means, int64_t P, int64_t G,
 int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int32_t P,
                            uint32_t *bins, int32_t *order, void *stream);
 
+/* One streaming pass over a count matrix X[n][ldx] (first G columns): per-cell total counts and
+ * zero counts, per-gene sum, sum of squares and zero counts.  These are the summaries the
+ * reference's notebooks compute with NumPy after sampling (library sizes X.sum(axis=1), zero
+ * fractions, per-gene mean/variance, e.g. examples/compare_axolotl.ipynb) and the full-size
+ * distribution check of the sampler.  All outputs are ADDED to (the caller zeroes them; any may be
+ * NULL).  Counts are taken as unsigned.  HBM-read bound, 4 B per count. */
+int pst_count_stats(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint64_t *cell_total,
+                    uint32_t *cell_zeros, uint64_t *gene_sum, uint64_t *gene_sumsq,
+                    uint64_t *gene_zeros, void *stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

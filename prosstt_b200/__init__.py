@@ -15,7 +15,7 @@ import sys
 __version__ = "0.1.0"
 
 from prosstt_b200 import _native  # noqa: F401  (binding only; the library loads lazily)
-from prosstt_b200 import tree, tree_utils, count_model, sim_utils, simulation, sharding  # noqa: F401
+from prosstt_b200 import tree, tree_utils, count_model, sim_utils, simulation, sharding, stats  # noqa: F401
 
 
 def install_as_prosstt():

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "pst_nb_params": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
     "pst_draw_counts": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _u64, _i64, _i64, _p, _i64, _p, _i32, _p, _p]),
     "pst_group_cells_by_row": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "pst_count_stats": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

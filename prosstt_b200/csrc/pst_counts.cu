@@ -539,9 +539,143 @@ __global__ void row_scatter_kernel(const int32_t *__restrict__ row_of_cell, int6
   }
 }
 
+// ---------------------------------------------------------------------------
+// One streaming pass over a count matrix: per-cell totals / zero counts and per-gene sum, sum of
+// squares and zero counts (the summary statistics every PROSSTT notebook computes after sampling,
+// and the full-size parity check of the sampler).  HBM-read bound: 4 B per count.
+// Same strip decomposition as the sampler: a warp owns 32 gene quads (512 B of a row) for a block
+// of rows; gene accumulators stay in registers, row partials are warp-reduced and added atomically.
+// ---------------------------------------------------------------------------
+constexpr int ST_ROWS = 256;                 // rows per chunk (8 groups of 32)
+constexpr int ST_BATCH = 8;                  // row loads in flight per thread
+
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2)
+count_stats_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx,
+                   unsigned long long *__restrict__ cell_total, unsigned int *__restrict__ cell_zeros,
+                   unsigned long long *__restrict__ gene_sum, unsigned long long *__restrict__ gene_sumsq,
+                   unsigned long long *__restrict__ gene_zeros) {
+  typedef unsigned long long ull;
+  const int lane = threadIdx.x & 31;
+  const int64_t Q = (G + 3) / 4;
+  const int64_t n_strips = (Q + 31) / 32;
+  const int64_t n_chunks = ((n + ST_ROWS - 1) / ST_ROWS) * n_strips;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t chunk = warp0; chunk < n_chunks; chunk += n_warps) {
+    const int64_t rgroup = chunk / n_strips;
+    const int64_t quad = (chunk - rgroup * n_strips) * 32 + lane;
+    const bool lane_ok = quad < Q;
+    const int64_t g0 = (lane_ok ? quad : 0) * 4;
+    const int64_t r_lo = rgroup * ST_ROWS;
+    const int64_t r_hi = min(n, r_lo + ST_ROWS);
+    ull s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    unsigned int z[4] = {0, 0, 0, 0};
+    for (int64_t rb = r_lo; rb < r_hi; rb += 16) {
+      // this lane's partial of 16 rows: total in bits 0..39, zero count in bits 40..47
+      ull part[16];
+#pragma unroll
+      for (int b0 = 0; b0 < 16; b0 += ST_BATCH) {
+        int4 q[ST_BATCH];
+#pragma unroll
+        for (int i = 0; i < ST_BATCH; ++i) {
+          const int64_t r = rb + b0 + i;
+          q[i] = make_int4(0, 0, 0, 0);
+          if (lane_ok && r < r_hi) {
+            if (VEC) {
+              q[i] = __ldcs(reinterpret_cast<const int4 *>(X + r * ldx + g0));
+            } else {
+              const int32_t *src = X + r * ldx + g0;
+              q[i].x = src[0];
+              if (g0 + 1 < G) q[i].y = src[1];
+              if (g0 + 2 < G) q[i].z = src[2];
+              if (g0 + 3 < G) q[i].w = src[3];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < ST_BATCH; ++i) {
+          const bool row_in = lane_ok && (rb + b0 + i < r_hi);
+          const unsigned int v[4] = {(unsigned int)q[i].x, (unsigned int)q[i].y, (unsigned int)q[i].z,
+                                     (unsigned int)q[i].w};
+          ull rt = 0;
+          unsigned int rz = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool in = row_in && (VEC || g0 + j < G);
+            s[j] += v[j];
+            ss[j] += (ull)v[j] * v[j];
+            const unsigned int zero = (in && v[j] == 0u) ? 1u : 0u;
+            z[j] += zero;
+            rt += v[j];
+            rz += zero;
+          }
+          part[b0 + i] = rt | ((ull)rz << 40);
+        }
+      }
+      // transpose-reduce: 15 exchanges leave the sum over each 16-lane half of row (rb + lane%16)
+      // in part[0]; one more exchange adds the two halves
+#pragma unroll
+      for (int half = 8; half > 0; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const ull send = upper ? part[i] : part[i + half];
+          const ull keep = upper ? part[i + half] : part[i];
+          const unsigned int lo = __shfl_xor_sync(0xffffffffu, (unsigned int)send, half);
+          const unsigned int hi = __shfl_xor_sync(0xffffffffu, (unsigned int)(send >> 32), half);
+          part[i] = keep + (((ull)hi << 32) | lo);
+        }
+      }
+      {
+        const unsigned int lo = __shfl_xor_sync(0xffffffffu, (unsigned int)part[0], 16);
+        const unsigned int hi = __shfl_xor_sync(0xffffffffu, (unsigned int)(part[0] >> 32), 16);
+        part[0] += ((ull)hi << 32) | lo;
+      }
+      const int64_t r = rb + (lane & 15);
+      if (lane < 16 && r < r_hi) {
+        if (cell_total) atomicAdd(cell_total + r, part[0] & 0xFFFFFFFFFFull);
+        if (cell_zeros) atomicAdd(cell_zeros + r, (unsigned int)(part[0] >> 40));
+      }
+    }
+    if (lane_ok) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (VEC || g0 + j < G) {
+          if (gene_sum) atomicAdd(gene_sum + g0 + j, s[j]);
+          if (gene_sumsq) atomicAdd(gene_sumsq + g0 + j, ss[j]);
+          if (gene_zeros) atomicAdd(gene_zeros + g0 + j, (ull)z[j]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace pst
 
 using namespace pst;
+
+extern "C" int pst_count_stats(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint64_t *cell_total,
+                               uint32_t *cell_zeros, uint64_t *gene_sum, uint64_t *gene_sumsq,
+                               uint64_t *gene_zeros, void *stream) {
+  const char *fn = "pst_count_stats";
+  PST_REQUIRE(n >= 0 && G >= 0 && ldx >= G, fn, "need n, G >= 0 and ldx >= G");
+  if (n == 0 || G == 0) return 0;
+  PST_REQUIRE(X, fn, "null pointer");
+  const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
+  const int64_t n_chunks = ((n + ST_ROWS - 1) / ST_ROWS) * ((((G + 3) / 4) + 31) / 32);
+  const int64_t need = (n_chunks + 7) / 8;                        // 8 warps per CTA
+  const unsigned blocks = (unsigned)std::min<int64_t>(need, (int64_t)kNumSM * 2);   // 2 CTAs of 8 warps per SM
+  typedef unsigned long long ull;
+  if (vec)
+    count_stats_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        X, n, G, ldx, (ull *)cell_total, cell_zeros, (ull *)gene_sum, (ull *)gene_sumsq, (ull *)gene_zeros);
+  else
+    count_stats_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        X, n, G, ldx, (ull *)cell_total, cell_zeros, (ull *)gene_sum, (ull *)gene_sumsq, (ull *)gene_zeros);
+  return check_launch(fn);
+}
+
 
 extern "C" int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int32_t P,
                                       uint32_t *bins, int32_t *order, void *stream) {

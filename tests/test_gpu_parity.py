@@ -733,3 +733,71 @@ def test_density_index_matches_numpy_searchsorted_at_scale():
     o = order.cpu().numpy()
     assert np.array_equal(np.sort(o), np.arange(n))
     assert np.all(np.diff(rows.cpu().numpy()[o]) >= 0)
+
+
+def test_count_stats_kernel_matches_numpy():
+    from prosstt_b200.stats import count_stats, gene_mean_var
+    rng = np.random.RandomState(6)
+    for n, G in ((1000, 403), (777, 4096), (3, 8)):
+        Xh = rng.negative_binomial(0.7, 0.1, size=(n, G)).astype(np.int32)
+        Xh[rng.random_sample((n, G)) < 0.3] = 0
+        st = count_stats(torch.from_numpy(Xh).to(DEV))
+        assert np.array_equal(st["cell_total"].cpu().numpy(), Xh.sum(axis=1, dtype=np.int64))
+        assert np.array_equal(st["cell_zeros"].cpu().numpy(), (Xh == 0).sum(axis=1))
+        assert np.array_equal(st["gene_sum"].cpu().numpy(), Xh.sum(axis=0, dtype=np.int64))
+        assert np.array_equal(st["gene_sumsq"].cpu().numpy(), (Xh.astype(np.int64) ** 2).sum(axis=0))
+        assert np.array_equal(st["gene_zeros"].cpu().numpy(), (Xh == 0).sum(axis=0))
+        mean, var = gene_mean_var(st, n)
+        assert np.allclose(mean.cpu().numpy(), Xh.mean(axis=0)) and np.allclose(var.cpu().numpy(), Xh.var(axis=0))
+    # padded rows: only the first G columns count
+    Xp = torch.full((50, 24), 7, dtype=torch.int32, device=DEV)
+    st = count_stats(Xp[:, :20])
+    assert st["cell_total"].tolist() == [140] * 50 and st["gene_sum"].tolist() == [350] * 20
+
+
+def test_full_size_config4_distribution_on_device():
+    """BASELINE config 4 at FULL size on one GPU (15 branches, G = 20 000, 1M cells = 2e10 counts,
+    80 GB): per-gene and per-cell totals against the model mean/variance, zero fraction against
+    (1+theta)^-r, all computed on the device (pst_count_stats + small P x G reductions)."""
+    if torch.cuda.get_device_properties(0).total_memory < 120e9:
+        pytest.skip("needs the 180 GB of a B200")
+    from prosstt_b200.session import DensitySession
+    from prosstt_b200.stats import count_stats
+    t, alpha, beta = _bench_like_tree(7, 50, 10, 20000, seed=42)
+    N = 1000000
+    sess = DensitySession(t, alpha, beta, N, device=DEV)
+    sess.step(44)
+    sess.engine.check()
+    st = count_stats(sess.X)
+    M = sess.engine.means.double()                                     # (P, G)
+    a = torch.from_numpy(alpha).to(DEV)
+    b = torch.from_numpy(beta).to(DEV)
+    rows = sess.rows.long()
+    s = sess.s64
+    P = M.shape[0]
+    w1 = torch.zeros(P, dtype=torch.float64, device=DEV).index_add_(0, rows, s)
+    w2 = torch.zeros(P, dtype=torch.float64, device=DEV).index_add_(0, rows, s * s)
+    # per gene: sum_cells mu and sum_cells (alpha mu^2 + beta mu)
+    e_gene = w1 @ M
+    v_gene = a * (w2 @ (M * M)) + b * e_gene
+    zg = (st["gene_sum"].double() - e_gene) / torch.sqrt(v_gene)
+    assert abs(zg.mean().item()) < 0.05 and 0.95 < zg.std().item() < 1.05, (zg.mean().item(), zg.std().item())
+    assert zg.abs().max().item() < 6.5
+    # per cell: s * sum_g M[row] and s^2 sum_g alpha M^2 + s sum_g beta M
+    r1 = M.sum(dim=1)
+    ra = (M * M) @ a
+    rb = M @ b
+    e_cell = s * r1[rows]
+    v_cell = s * s * ra[rows] + s * rb[rows]
+    zc = (st["cell_total"].double() - e_cell) / torch.sqrt(v_cell)
+    assert abs(zc.mean().item()) < 0.01 and 0.99 < zc.std().item() < 1.01, (zc.mean().item(), zc.std().item())
+    # zero fraction: mean over a 4000-cell sample of prod-free expectation (1+theta)^-r
+    idx = torch.randperm(N, device=DEV)[:4000]
+    mu = M[rows[idx]] * s[idx, None]
+    theta = a * mu + b - 1
+    p0 = torch.exp(-mu / theta * torch.log1p(theta)).sum(dim=1)
+    got0 = st["cell_zeros"][idx].double()
+    zz = (got0.sum() - p0.sum()) / torch.sqrt((p0 / 20000 * (1 - p0 / 20000)).sum() * 20000)
+    assert abs(zz.item()) < 5, zz.item()
+    total = int(st["cell_total"].sum().item())
+    assert total == int(st["gene_sum"].sum().item())                   # the two marginals agree
