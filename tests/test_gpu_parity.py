@@ -801,3 +801,35 @@ def test_full_size_config4_distribution_on_device():
     assert abs(zz.item()) < 5, zz.item()
     total = int(st["cell_total"].sum().item())
     assert total == int(st["gene_sum"].sum().item())                   # the two marginals agree
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_random_parameter_sweep(sampler):
+    """4000 random (mu, alpha, beta) triples over 8 decades of mu and 3.5 of alpha: the per-gene
+    mean z-scores must look standard normal and the variance ratios must centre on 1 - catches a
+    bias confined to any corner of the parameter space (route boundaries, r << 1, theta -> 0)."""
+    import scipy.stats
+    from prosstt_b200.stats import count_stats, gene_mean_var
+    rng = np.random.RandomState(99)
+    G, N = 4000, 60000
+    mu = np.exp(rng.uniform(np.log(1e-4), np.log(3e3), size=G))
+    alpha = np.exp(rng.uniform(np.log(1e-3), np.log(3.0), size=G))
+    beta = 1 + np.exp(rng.uniform(np.log(1e-6), np.log(10.0), size=G))
+    alpha[:200] = 0.0                                           # Poisson-like corner
+    t = _flat_tree(mu)
+    dev = torch.device(DEV)
+    eng = CountEngine(t, TreeTables(t, dev), alpha, beta, dev, sampler=sampler)
+    X = eng.draw(torch.zeros(N, dtype=torch.int32, device=dev), torch.ones(N, dtype=torch.float32, device=dev), 2718, 0)
+    eng.check()
+    mean, var = gene_mean_var(count_stats(X), N)
+    mean, var = mean.cpu().numpy(), var.cpu().numpy()
+    true_var = alpha * mu ** 2 + beta * mu
+    z = (mean - mu) / np.sqrt(true_var / N)
+    assert scipy.stats.kstest(z, "norm").pvalue > 1e-4, (z.mean(), z.std())
+    assert abs(z.mean()) < 0.08 and 0.93 < z.std() < 1.07 and np.abs(z).max() < 5.5, (z.mean(), z.std(), np.abs(z).max())
+    # variance: compare on genes with enough events; the ratio's spread depends on the kurtosis,
+    # so test the median and the bulk
+    ok = mu * N > 200
+    ratio = var[ok] / true_var[ok]
+    assert abs(np.median(ratio) - 1) < 0.01, np.median(ratio)
+    assert np.mean(np.abs(ratio - 1) < 0.25) > 0.97
