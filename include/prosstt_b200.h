@@ -147,6 +147,15 @@ int pst_whole_tree_index(const int32_t *cover_pt, const int32_t *cover_branch,
  * kernel); z=NULL writes ones (scale=False).  Replaces sim_utils.py:494-498. */
 int pst_scalings(const double *z, int64_t n, double *out64, float *out32, void *stream);
 
+/* per-gene base expression exp(N(gene_mean, gene_std)), redrawn while base * cap[g] > abs_max
+ * (cap = max over the tree of exp(relative mean), from pst_rel_means' out_colmax).  Replaces
+ * sim_utils.py:463-469; attempt a of gene g uses the normal at element a*G + g.  out_tries
+ * (optional) = draws consumed per gene; PST_FLAG_DOMAIN is set in flags[0] if a gene is still
+ * above abs_max after max_tries draws. */
+int pst_base_gene_exp(uint64_t seed, uint32_t tag, const double *cap, int64_t G, double abs_max,
+                      double gene_mean, double gene_std, int32_t max_tries, double *out_base,
+                      int32_t *out_tries, uint32_t *flags, void *stream);
+
 /* ---- count model: count_model.py:131-161 ------------------------------------- */
 /* fp64 (p, r) of get_pr_umi for mu[n_cells][G] with per-gene alpha/beta - parity hook
  * for the parameterisation that pst_draw_counts fuses in fp32. */
@@ -192,6 +201,22 @@ int pst_count_stats(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint64_
                     uint64_t *gene_zeros, void *stream);
 
 #if defined(__GNUC__)
+/* ---- epilogues over the count matrix ------------------- */
+#define PST_TRANSFORM_NORMALIZE        0   /* X / scaling            (compare_axolotl.ipynb cell 14) */
+#define PST_TRANSFORM_NORMALIZE_LOG1P  1   /* log(X / scaling + 1)                                   */
+#define PST_TRANSFORM_LOG1P            2   /* log(X + 1)             (minimal_example.ipynb cell 6)  */
+/* out[i][g] = f(X[i][g], scaling[i]) as fp32, row strides ldx / ldo elements.  scaling may be
+ * NULL for PST_TRANSFORM_LOG1P. */
+int pst_transform_counts(const int32_t *X, int64_t n, int64_t G, int64_t ldx, const float *scaling,
+                         int32_t mode, float *out, int64_t ldo, void *stream);
+/* Compact the dense (n, G) matrix into CSR: for row i the nonzero columns (ascending) and values
+ * go to indices/data[indptr[i] .. indptr[i+1]).  indptr (n+1 entries, device) is the exclusive
+ * scan of the per-row nonzero counts, i.e. G - cell_zeros from pst_count_stats.  Sets
+ * PST_FLAG_ROW in flags[0] if indptr does not match the matrix (nothing is written past a
+ * row's end).  Replaces the dense text dump of tree_utils.py:111-121 as the exchange format. */
+int pst_csr_fill(const int32_t *X, int64_t n, int64_t G, int64_t ldx, const int64_t *indptr,
+                 int32_t *indices, int32_t *data, uint32_t *flags, void *stream);
+
 #pragma GCC visibility pop
 #endif
 #ifdef __cplusplus

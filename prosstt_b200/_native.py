@@ -18,9 +18,9 @@ SAMPLER_GAMMA_POISSON, SAMPLER_HYBRID = 0, 1
 SAMPLERS = {"gamma_poisson": SAMPLER_GAMMA_POISSON, "hybrid": SAMPLER_HYBRID}
 
 # user-visible stream tags (third Philox counter word); < 0x100 by convention
-TAG_DENSITY_U, TAG_SERIES_Z, TAG_PICK_U, TAG_SCALING_Z = 1, 2, 3, 4
+TAG_DENSITY_U, TAG_SERIES_Z, TAG_PICK_U, TAG_SCALING_Z, TAG_BASE_Z = 1, 2, 3, 4, 5
 
-_p, _i32, _i64, _u32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+_p, _i32, _i64, _u32, _u64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
 
 _SIGNATURES = {
     "pst_abi_version": (C.c_int, []),
@@ -41,10 +41,13 @@ _SIGNATURES = {
     "pst_rows_from_branch": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "pst_whole_tree_index": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "pst_scalings": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "pst_base_gene_exp": (C.c_int, [_u64, _u32, _p, _i64, _f64, _f64, _f64, _i32, _p, _p, _p, _p]),
     "pst_nb_params": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
     "pst_draw_counts": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _u64, _i64, _i64, _p, _i64, _p, _i32, _p, _p]),
     "pst_group_cells_by_row": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "pst_count_stats": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "pst_transform_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p]),
+    "pst_csr_fill": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -194,6 +194,27 @@ __global__ void scalings_kernel(const double *__restrict__ z, int64_t n, double 
   }
 }
 
+// sim_utils.py:463-469 with the redraws as counter-based attempts: attempt a of gene g reads the
+// normal at element a*G + g, so the result does not depend on the launch shape
+__global__ void base_gene_exp_kernel(PhiloxKey key, uint32_t tag, const double *__restrict__ cap, int64_t G,
+                                     double abs_max, double gene_mean, double gene_std, int max_tries,
+                                     double *__restrict__ out_base, int32_t *__restrict__ out_tries,
+                                     uint32_t *__restrict__ flags) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const double c = cap[g];
+    double value = 0.0;
+    int a = 0;
+    for (; a < max_tries; ++a) {
+      value = exp(gene_mean + gene_std * normal_f64(element_block(key, tag, (int64_t)a * G + g)));
+      if (!(value * c > abs_max)) break;
+    }
+    if (a == max_tries) atomicOr(flags, (uint32_t)PST_FLAG_DOMAIN);
+    out_base[g] = value;
+    if (out_tries) out_tries[g] = a + 1;
+  }
+}
+
 __global__ void nb_params_kernel(const double *__restrict__ alpha, const double *__restrict__ beta,
                                  const double *__restrict__ mu, int64_t n_cells, int64_t G,
                                  double *__restrict__ out_p, double *__restrict__ out_r) {
@@ -333,6 +354,20 @@ extern "C" int pst_scalings(const double *z, int64_t n, double *out64, float *ou
   if (n == 0) return 0;
   PST_REQUIRE(out64 || out32, fn, "no output");
   scalings_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(z, n, out64, out32);
+  return check_launch(fn);
+}
+
+extern "C" int pst_base_gene_exp(uint64_t seed, uint32_t tag, const double *cap, int64_t G, double abs_max,
+                                 double gene_mean, double gene_std, int32_t max_tries, double *out_base,
+                                 int32_t *out_tries, uint32_t *flags, void *stream) {
+  const char *fn = "pst_base_gene_exp";
+  PST_REQUIRE(G >= 0, fn, "negative size");
+  if (G == 0) return 0;
+  PST_REQUIRE(cap && out_base && flags, fn, "null pointer");
+  PST_REQUIRE(max_tries > 0, fn, "max_tries must be positive");
+  base_gene_exp_kernel<<<grid_for(G), 256, 0, (cudaStream_t)stream>>>(PhiloxKey(seed), tag, cap, G, abs_max,
+                                                                      gene_mean, gene_std, max_tries, out_base,
+                                                                      out_tries, flags);
   return check_launch(fn);
 }
 

@@ -163,14 +163,39 @@ def max_relat_exp(tree, relative_means):
                      for b in tree.branches], axis=1)
 
 
-def simulate_base_gene_exp(tree, relative_means, abs_max=5000, gene_mean=0.8, gene_std=1):
+def base_gene_exp_on_device(cap, seed, abs_max=5000, gene_mean=0.8, gene_std=1, max_tries=100000):
+    """Device form of the redraw loop (sim_utils.py:463-469): `cap` is the (G,) fp64 device vector
+    of max exp(relative mean); attempt a of gene g reads the Philox normal at element a*G + g of
+    the stream keyed by `seed`.  Returns the (G,) fp64 device vector of base expressions."""
+    G = cap.numel()
+    dev = cap.device
+    base = torch.empty(G, dtype=torch.float64, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    nat.call("pst_base_gene_exp", nat.split_seed(seed), nat.TAG_BASE_Z, cap, G, float(abs_max),
+             float(gene_mean), float(gene_std), int(max_tries), base, None, flags, nat.stream_ptr(dev))
+    if int(flags.item()) != 0:
+        raise RuntimeError("a gene cannot satisfy abs_max=%g within %d draws" % (abs_max, max_tries))
+    return base
+
+
+def simulate_base_gene_exp(tree, relative_means, abs_max=5000, gene_mean=0.8, gene_std=1, seed=None,
+                           device=None):
     """Per-gene base expression exp(N(gene_mean, gene_std)), redrawn while
-    base * max relative expression > abs_max (sim_utils.py:429-470).  O(G) host-side setup
-    on the global legacy numpy stream; the draw order (gene by gene, redraws in place) is
-    the reference's, so np.random.seed(s) reproduces its values."""
+    base * max relative expression > abs_max (sim_utils.py:429-470).  With seed=None this is the
+    O(G) host loop on the global legacy numpy stream in the reference's draw order (gene by gene,
+    redraws in place), so np.random.seed(s) reproduces its values; with a seed the draws are
+    counter-based and run on the device (base_gene_exp_on_device)."""
     cap = np.max(max_relat_exp(tree, relative_means), axis=1)
-    base = np.zeros(tree.G)
-    for gene in range(tree.G):
+    if seed is not None:
+        dev = nat.device(device)
+        return base_gene_exp_on_device(nat.to_dev(cap, torch.float64, dev), seed, abs_max, gene_mean,
+                                       gene_std).cpu().numpy()
+    return _base_gene_exp_legacy(cap, abs_max, gene_mean, gene_std)
+
+
+def _base_gene_exp_legacy(cap, abs_max, gene_mean, gene_std):
+    base = np.zeros(len(cap))
+    for gene in range(len(cap)):
         value = np.exp(np.random.normal(gene_mean, gene_std))
         tries = 0
         while value * cap[gene] > abs_max:

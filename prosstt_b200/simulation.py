@@ -248,29 +248,25 @@ class DeviceMeans(object):
 
 
 def default_gene_expression_on_device(tree, seed=None, device=None, abs_max=5000, gene_mean=0.8,
-                                      gene_std=1, **kwargs):
+                                      gene_std=1, base_seed=None, **kwargs):
     """simulate_lineage + simulate_base_gene_exp + exp(rel)*scale + add_genes (tree.py:436-446)
-    without the host round trip of the (P, G) tables: the per-gene maximum comes from the device,
-    the O(G) base-expression draw stays on the host (global legacy stream, reference draw order),
-    and the means table is built in HBM.  Sets tree.means to a DeviceMeans.  Returns
-    (H, gene_scale)."""
+    without the host round trip of the (P, G) tables: the per-gene maximum comes from the device
+    and the means table is built in HBM.  The O(G) base-expression draw runs on the host (global
+    legacy stream, reference draw order) unless `base_seed` is given, in which case it is the
+    counter-based device draw (sut.base_gene_exp_on_device).  Sets tree.means to a DeviceMeans.
+    Returns (H, gene_scale)."""
     kwargs.setdefault("a", 0.05)
     state, H = simulate_lineage(tree, seed=seed, device=device, _return_state=True, **kwargs)
     dev, tb = state.dev, state.tables
     st = nat.stream_ptr(dev)
     # max over the tree of exp(rel) per gene (sim_utils.py:406-426,461): exp is monotone
-    cap = torch.exp(state.rel.max(dim=0).values).cpu().numpy()
-    base = np.zeros(tree.G)
-    for gene in range(tree.G):                                   # sim_utils.py:463-469
-        value = np.exp(np.random.normal(gene_mean, gene_std))
-        tries = 0
-        while value * cap[gene] > abs_max:
-            tries += 1
-            if tries > 100000:
-                raise RuntimeError("gene %d cannot satisfy abs_max=%g" % (gene, abs_max))
-            value = np.exp(np.random.normal(gene_mean, gene_std))
-        base[gene] = value
-    scale = nat.to_dev(base, torch.float64, dev)
+    cap = torch.exp(state.rel.max(dim=0).values)
+    if base_seed is not None:
+        scale = sut.base_gene_exp_on_device(cap, base_seed, abs_max, gene_mean, gene_std)
+        base = scale.cpu().numpy()
+    else:
+        base = sut._base_gene_exp_legacy(cap.cpu().numpy(), abs_max, gene_mean, gene_std)  # sim_utils.py:463-469
+        scale = nat.to_dev(base, torch.float64, dev)
     table32 = torch.empty((tb.P, state.G), dtype=torch.float32, device=dev)
     nat.call("pst_rel_means", nat.ptr(state.W), nat.ptr(state.H), nat.ptr(scale), 0, tb.P, state.K, state.G,
              None, None, nat.ptr(table32), None, st)

@@ -833,3 +833,131 @@ def test_random_parameter_sweep(sampler):
     ratio = var[ok] / true_var[ok]
     assert abs(np.median(ratio) - 1) < 0.01, np.median(ratio)
     assert np.mean(np.abs(ratio - 1) < 0.25) > 0.97
+
+
+# ------------------------------------------------------------------ 8f "next" rows: base expression, epilogues, formats
+def test_base_gene_exp_on_device_matches_oracle():
+    """sim_utils.py:463-469 with counter-based redraws: attempt a of gene g consumes the normal at
+    element a*G + g.  Replay exactly those normals through the oracle's sequential loop."""
+    dev = torch.device(DEV)
+    G, seed, mean, std, abs_max = 5000, 99, 0.8, 1.0, 5000.0
+    rng = np.random.RandomState(1)
+    cap = np.exp(rng.uniform(0, 8, G))                      # max exp(rel) up to the cutoff e^8
+    cap[::50] = 4000.0                                      # genes that need many redraws
+    base = torch.empty(G, dtype=torch.float64, device=dev)
+    tries = torch.empty(G, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    nat.call("pst_base_gene_exp", seed, nat.TAG_BASE_Z, _dev(cap, torch.float64), G, abs_max, mean, std, 1000,
+             base, tries, flags, nat.stream_ptr(dev))
+    assert int(flags.item()) == 0
+    tries_h = tries.cpu().numpy()
+    A = int(tries_h.max())
+    assert A > 3                                            # the redraw path is exercised
+    z = torch.empty((A, G), dtype=torch.float64, device=dev)
+    nat.call("pst_normal_f64", seed, nat.TAG_BASE_Z, 0, A * G, mean, std, None, None, z, nat.stream_ptr(dev))
+    zh = z.cpu().numpy()
+    want = np.zeros(G)
+    used = np.zeros(G, dtype=np.int64)
+    for g in range(G):
+        out, n_used = orc.base_gene_exp_from_normals(cap[g:g + 1], zh[:, g], abs_max)
+        want[g], used[g] = out[0], n_used
+    assert np.array_equal(tries_h, used)
+    assert np.allclose(base.cpu().numpy(), want, rtol=1e-12, atol=0)
+    assert np.all(want * cap <= abs_max)
+    # through the reference-shaped API, and the failure report
+    t = ptree.Tree(topology=[[0, 1], [0, 2]], time={0: 5, 1: 5, 2: 5}, num_branches=3, branch_points=1, modules=4, G=40)
+    rel = {b: rng.normal(0, 1, (5, 40)) for b in t.branches}
+    got = sut.simulate_base_gene_exp(t, rel, seed=7, device=DEV)
+    again = sut.simulate_base_gene_exp(t, rel, seed=7, device=DEV)
+    assert got.shape == (40,) and np.array_equal(got, again)
+    assert np.all(got * np.max(sut.max_relat_exp(t, rel), axis=1) <= 5000)
+    with pytest.raises(RuntimeError):
+        sut.base_gene_exp_on_device(_dev(np.full(8, 1e30), torch.float64), 3, max_tries=50)
+
+
+def test_default_gene_expression_with_device_base_draw():
+    t = ptree.Tree(topology=[[0, 1], [0, 2]], time={0: 20, 1: 20, 2: 20}, num_branches=3, branch_points=1, modules=6,
+                   G=300)
+    np.random.seed(4)                                      # H comes from the host legacy stream
+    H, base = sim.default_gene_expression_on_device(t, seed=5, device=DEV, base_seed=6)
+    np.random.seed(4)
+    H2, base2 = sim.default_gene_expression_on_device(t, seed=5, device=DEV, base_seed=6)
+    assert np.array_equal(base, base2) and np.array_equal(H, H2)
+    mx = max(np.max(t.means[b]) for b in t.branches)
+    assert mx <= 5000 * (1 + 1e-6)
+    assert abs(np.log(base).mean() - 0.8) < 0.5            # lognormal(0.8, 1) truncated from above
+
+
+def test_transform_counts_matches_numpy():
+    from prosstt_b200 import stats as pstats
+    rng = np.random.RandomState(8)
+    for n, G in ((300, 403), (257, 1024), (2, 4)):
+        Xh = rng.negative_binomial(0.7, 0.05, size=(n, G)).astype(np.int32)
+        s = np.exp(rng.normal(0, 0.7, n))
+        X = torch.from_numpy(Xh).to(DEV)
+        s32 = s.astype(np.float32).astype(np.float64)       # the kernel divides by the fp32 scaling
+        norm = (Xh.T / s32).T                               # compare_axolotl.ipynb cell 14
+        assert np.allclose(pstats.normalize(X, s).cpu().numpy(), norm, rtol=2e-7, atol=0)
+        assert np.allclose(pstats.normalize(X, s, log=True).cpu().numpy(), np.log(norm + 1), rtol=1e-6, atol=1e-7)
+        assert np.allclose(pstats.log1p(X).cpu().numpy(), np.log(Xh + 1.0), rtol=1e-6, atol=1e-7)
+    # padded input and output rows
+    Xp = torch.arange(50 * 24, dtype=torch.int32, device=DEV).reshape(50, 24)
+    out = torch.full((50, 32), -1.0, dtype=torch.float32, device=DEV)
+    pstats.transform_counts(Xp[:, :20], mode="log1p", out=out[:, :20])
+    assert torch.allclose(out[:, :20], torch.log1p(Xp[:, :20].float())) and bool((out[:, 20:] == -1).all())
+    with pytest.raises(ValueError):
+        pstats.transform_counts(Xp, None, "normalize")
+    with pytest.raises(ValueError):                        # unknown mode: invalid-argument status
+        nat.call("pst_transform_counts", Xp.data_ptr(), 50, 24, 24, None, 9, out.data_ptr(), 32,
+                 nat.stream_ptr(torch.device(DEV)))
+
+
+def test_csr_compaction_matches_scipy(tmp_path):
+    import scipy.sparse as sp
+    from prosstt_b200 import formats
+    rng = np.random.RandomState(9)
+    for n, G, zero_frac in ((500, 403, 0.5), (129, 2048, 0.9), (64, 128, 0.0), (5, 7, 1.0)):
+        Xh = (rng.negative_binomial(0.7, 0.05, size=(n, G)) + 1).astype(np.int32)
+        Xh[rng.random_sample((n, G)) < zero_frac] = 0
+        if zero_frac == 1.0:
+            Xh[:] = 0
+        Xh[n // 2] = 0                                       # an empty row
+        indptr, indices, data = formats.to_csr(torch.from_numpy(Xh).to(DEV))
+        want = sp.csr_matrix(Xh)
+        want.sort_indices()
+        assert np.array_equal(indptr.cpu().numpy(), want.indptr)
+        assert np.array_equal(indices.cpu().numpy(), want.indices)
+        assert np.array_equal(data.cpu().numpy(), want.data)
+    # padded stride, file round trip through scipy's own reader
+    Xh_pad = rng.poisson(0.5, size=(40, 24)).astype(np.int32)
+    Xp = torch.from_numpy(Xh_pad).to(DEV)
+    path = formats.save_sparse_npz(str(tmp_path / "counts"), Xp[:, :21])
+    back = sp.load_npz(path)
+    assert back.shape == (40, 21) and np.array_equal(back.toarray(), Xh_pad[:, :21])
+    ip, ix, da, shape = formats.load_sparse_npz(path)
+    assert np.array_equal(formats.csr_to_dense(ip, ix, da, shape), Xh_pad[:, :21])
+    # a stale row pointer is reported, not written past
+    X = torch.from_numpy(Xh_pad).to(DEV)
+    bad = torch.zeros(41, dtype=torch.int64, device=DEV)
+    flags = torch.zeros(1, dtype=torch.int32, device=DEV)
+    buf = torch.zeros(8, dtype=torch.int32, device=DEV)
+    nat.call("pst_csr_fill", X.data_ptr(), 40, 24, 24, bad, buf, buf.clone(), flags, nat.stream_ptr(torch.device(DEV)))
+    assert int(flags.item()) != 0 and bool((buf == 0).all())
+
+
+def test_sampled_counts_to_csr_and_npy_shards(tmp_path):
+    """Sampler output -> CSR on the device and dense .npy shards from the streamed host buffers."""
+    from prosstt_b200 import formats
+    t, alpha, beta = _bench_like_tree(2, 20, 6, 1000, seed=3)
+    X, pt, br, sc = sim.sample_density(t, 3000, alpha, beta, seed=12, device=DEV, dtype=np.int32)
+    indptr, indices, data = formats.to_csr(torch.from_numpy(np.ascontiguousarray(X)).to(DEV))
+    assert np.array_equal(formats.csr_to_dense(indptr.cpu().numpy(), indices.cpu().numpy(), data.cpu().numpy(), X.shape), X)
+    parts = []
+    for rank in range(2):
+        Xr = sim.sample_density(t, 3000, alpha, beta, seed=12, device=DEV, dtype=np.int32, shard=(rank, 2))[0]
+        path = formats.shard_path(str(tmp_path / "sim"), rank, 2)
+        with formats.NpyShardWriter(path, Xr.shape[0], Xr.shape[1]) as w:
+            for lo in range(0, Xr.shape[0], 700):
+                w.append(Xr[lo:lo + 700])
+        parts.append(np.load(path, mmap_mode="r"))
+    assert np.array_equal(np.concatenate(parts, axis=0), X)

@@ -207,3 +207,32 @@ def test_text_writers_round_trip(tmp_path):
     assert list(genes.columns) == ["alpha", "beta", "genescale"]
     text = (tmp_path / "job_params.txt").read_text()
     assert "Genes: 4" in text and "#modules: 3" in text and text.endswith("random seed: 7")
+
+
+def test_binary_formats_host_side(tmp_path):
+    """formats.NpyShardWriter writes a valid .npy in row blocks; load_sparse_npz reads scipy's layout."""
+    import scipy.sparse as sp
+    from prosstt_b200 import formats
+    X = np.arange(35, dtype=np.int32).reshape(7, 5)
+    path = formats.shard_path(str(tmp_path / "sim"), 0, 1)
+    assert path.endswith("sim.npy") and formats.shard_path("s", 3, 8) == "s.rank3of8.npy"
+    with formats.NpyShardWriter(path, 7, 5) as w:
+        w.append(X[:3])
+        w.append(X[3:])
+    assert np.array_equal(np.load(path), X) and np.load(path).dtype == np.int32
+    w = formats.NpyShardWriter(str(tmp_path / "short.npy"), 7, 5)
+    w.append(X[:3])
+    with pytest.raises(ValueError):
+        w.close()                                          # rows missing
+    w = formats.NpyShardWriter(str(tmp_path / "long.npy"), 2, 5)
+    with pytest.raises(ValueError):
+        w.append(X)                                        # too many rows
+    with pytest.raises(ValueError):
+        w.append(X[:1, :4])                                # wrong width
+    m = sp.csr_matrix(np.array([[0, 2, 0], [0, 0, 0], [5, 0, 7]], dtype=np.int32))
+    sp.save_npz(str(tmp_path / "m.npz"), m)
+    ip, ix, da, shape = formats.load_sparse_npz(str(tmp_path / "m.npz"))
+    assert shape == (3, 3) and np.array_equal(formats.csr_to_dense(ip, ix, da, shape), m.toarray())
+    sp.save_npz(str(tmp_path / "c.npz"), m.tocsc())
+    with pytest.raises(ValueError):
+        formats.load_sparse_npz(str(tmp_path / "c.npz"))
