@@ -97,6 +97,46 @@ csr_fill_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// uint16 transfer format: out = min(X, 65535); every element that reads 65535 also has an entry
+// (flat index, exact value) in the overflow list, so the int32 matrix can be rebuilt exactly
+// ---------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+narrow_u16_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx,
+                  uint16_t *__restrict__ out, int64_t ldo, int64_t row0, int64_t *__restrict__ ovf_index,
+                  int32_t *__restrict__ ovf_value, int64_t ovf_cap, unsigned long long *__restrict__ ovf_count) {
+  const int64_t Q = (G + 3) / 4;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g0 = q * 4;
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
+      const int32_t *src = X + row * ldx + g0;
+      uint16_t *dst = out + row * ldo + g0;
+      int v[4] = {0, 0, 0, 0};
+      if (VEC) {
+        const int4 w = __ldcs(reinterpret_cast<const int4 *>(src));
+        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+      } else {
+        for (int j = 0; j < 4 && g0 + j < G; ++j) v[j] = src[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (v[j] >= 65535 && g0 + j < G) {                            // rare: one atomic per overflowing count
+          const unsigned long long slot = atomicAdd(ovf_count, 1ull);
+          if ((int64_t)slot < ovf_cap) { ovf_index[slot] = (row0 + row) * G + g0 + j; ovf_value[slot] = v[j]; }
+          v[j] = 65535;
+        }
+      }
+      if (VEC) {
+        __stcs(reinterpret_cast<uint2 *>(dst), make_uint2((unsigned)v[0] | ((unsigned)v[1] << 16),
+                                                          (unsigned)v[2] | ((unsigned)v[3] << 16)));
+      } else {
+        for (int j = 0; j < 4 && g0 + j < G; ++j) dst[j] = (uint16_t)v[j];
+      }
+    }
+  }
+}
+
 inline unsigned stream_grid(int64_t threads) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, (int64_t)kNumSM * 16));
 }
@@ -144,5 +184,27 @@ extern "C" int pst_csr_fill(const int32_t *X, int64_t n, int64_t G, int64_t ldx,
   const unsigned grid = stream_grid(n * 32);
   if (vec) csr_fill_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, G, ldx, indptr, indices, data, flags);
   else csr_fill_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, G, ldx, indptr, indices, data, flags);
+  return check_launch(fn);
+}
+
+extern "C" int pst_narrow_counts_u16(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint16_t *out, int64_t ldo,
+                                     int64_t row0, int64_t *ovf_index, int32_t *ovf_value, int64_t ovf_cap,
+                                     uint64_t *ovf_count, void *stream) {
+  const char *fn = "pst_narrow_counts_u16";
+  PST_REQUIRE(n >= 0 && G >= 0 && ldx >= G && ldo >= G && row0 >= 0 && ovf_cap >= 0, fn,
+              "need n, G, row0, ovf_cap >= 0, ldx >= G and ldo >= G");
+  if (n == 0 || G == 0) return 0;
+  PST_REQUIRE(X && out && ovf_count && (ovf_cap == 0 || (ovf_index && ovf_value)), fn, "null pointer");
+  const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
+                   ((uintptr_t)out % 8 == 0);
+  const int64_t qblocks = std::min<int64_t>((((G + 3) / 4) + 255) / 256, 64);
+  const int64_t yblocks = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)kNumSM * 16 + qblocks - 1) / qblocks));
+  const dim3 grid((unsigned)qblocks, (unsigned)yblocks);
+  if (vec)
+    narrow_u16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, G, ldx, out, ldo, row0, ovf_index, ovf_value,
+                                                                    ovf_cap, (unsigned long long *)ovf_count);
+  else
+    narrow_u16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, G, ldx, out, ldo, row0, ovf_index, ovf_value,
+                                                                     ovf_cap, (unsigned long long *)ovf_count);
   return check_launch(fn);
 }

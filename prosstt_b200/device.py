@@ -187,6 +187,7 @@ class CountEngine(object):
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # status + scheduler scratch
         self.group_rows = not os.environ.get("PST_NO_GROUP")    # developer switch
         self._order = self._bins = None
+        self.overflow = None                                    # filled by draw_to_host (uint16 format)
 
     def draw(self, rows, scaling32, seed, cell0, out=None):
         """Sample X for the cells described by rows/scaling32 (device tensors); global
@@ -210,14 +211,23 @@ class CountEngine(object):
                  nat.ptr(self.flags), self.sampler, order, st)
         return out
 
-    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None):
-        """Sample in cell chunks and stream them into `host_out` (an (n, G) int32 CPU
-        tensor, ideally pinned): sampling of chunk i+1 overlaps the copy of chunk i."""
+    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=1 << 20):
+        """Sample in cell chunks and stream them into `host_out` (an (n, G) CPU tensor, ideally
+        pinned): sampling of chunk i+1 overlaps the copy of chunk i.
+
+        host_out.dtype int32: the counts as sampled (4 B per count over PCIe).
+        host_out.dtype uint16: the narrow transfer format (2 B per count): min(count, 65535), and
+        every element that reads 65535 is listed exactly in `self.overflow` = (flat index into
+        host_out, int32 value) NumPy arrays sorted by index (formats.widen_u16 rebuilds int32)."""
         n = int(rows.numel())
+        narrow = host_out.dtype == torch.uint16
+        if not narrow and host_out.dtype != torch.int32:
+            raise ValueError("host_out must be an int32 or uint16 CPU tensor")
+        width = 2 if narrow else 4
         if chunk_cells is None:
             # ~1 GiB copies keep the copy engine at its large-transfer rate; the first chunks are
             # smaller so that the device->host stream starts almost immediately
-            chunk_cells = max(1, min(n, (1 << 30) // max(1, 4 * self.G)))
+            chunk_cells = max(1, min(n, (1 << 30) // max(1, width * self.G)))
             ramp = [max(1, chunk_cells // 8), max(1, chunk_cells // 4), max(1, chunk_cells // 2)]
         else:
             ramp = []
@@ -226,15 +236,28 @@ class CountEngine(object):
             size = ramp.pop(0) if ramp else chunk_cells
             bounds.append((lo, min(n, lo + size)))
             lo = bounds[-1][1]
-        bufs = [torch.empty((chunk_cells, self.G), dtype=torch.int32, device=self.dev) for _ in range(2)]
+        # staging buffers (what the copy engine reads) are double-buffered; in the narrow format the
+        # int32 chunk is consumed by the narrowing kernel on the sampling stream, so one is enough
+        stage = [torch.empty((chunk_cells, self.G), dtype=host_out.dtype, device=self.dev) for _ in range(2)]
+        self.overflow = None
+        if narrow:
+            work = torch.empty((chunk_cells, self.G), dtype=torch.int32, device=self.dev)
+            ovf_index = torch.empty(max(1, overflow_cap), dtype=torch.int64, device=self.dev)
+            ovf_value = torch.empty(max(1, overflow_cap), dtype=torch.int32, device=self.dev)
+            ovf_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
         copy_stream = torch.cuda.Stream(device=self.dev)
         main = torch.cuda.current_stream(self.dev)
         free = [torch.cuda.Event(), torch.cuda.Event()]
         for i, (lo, hi) in enumerate(bounds):
-            buf = bufs[i & 1][:hi - lo]
+            buf = stage[i & 1][:hi - lo]
             if i >= 2:
                 main.wait_event(free[i & 1])
-            self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=buf)
+            if narrow:
+                self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=work[:hi - lo])
+                nat.call("pst_narrow_counts_u16", work.data_ptr(), hi - lo, self.G, self.G, buf.data_ptr(), self.G,
+                         lo, ovf_index, ovf_value, int(overflow_cap), ovf_count, nat.stream_ptr(self.dev))
+            else:
+                self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=buf)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_stream):
@@ -242,6 +265,15 @@ class CountEngine(object):
                 host_out[lo:hi].copy_(buf, non_blocking=True)
                 free[i & 1].record(copy_stream)
         copy_stream.synchronize()
+        if narrow:
+            count = int(ovf_count.item())
+            if count > overflow_cap:
+                raise OverflowError("%d counts exceed 65534 but the overflow list holds %d: use an int32 "
+                                    "host buffer or a larger overflow_cap" % (count, overflow_cap))
+            index = ovf_index[:count].cpu().numpy()
+            value = ovf_value[:count].cpu().numpy()
+            order = np.argsort(index, kind="stable")
+            self.overflow = (index[order], value[order])
         return host_out
 
     def check(self):

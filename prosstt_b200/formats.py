@@ -79,6 +79,22 @@ def csr_to_dense(indptr, indices, data, shape):
     return out
 
 
+def widen_u16(X16, overflow):
+    """Exact int32 matrix from the uint16 transfer format: X16 (n, G) uint16 with saturated
+    elements reading 65535, overflow = (flat index, value) arrays or the dict filled by
+    `sample_density(host_out=(..., dict))`."""
+    if isinstance(overflow, dict):
+        overflow = (overflow["index"], overflow["value"])
+    X16 = np.asarray(X16)
+    out = X16.astype(np.int32)
+    index, value = np.asarray(overflow[0]), np.asarray(overflow[1])
+    saturated = np.flatnonzero(X16.reshape(-1) == 65535)
+    if not np.array_equal(saturated, index):
+        raise ValueError("overflow list does not match the saturated elements of the matrix")
+    out.reshape(-1)[index] = value
+    return out
+
+
 class NpyShardWriter(object):
     """Append-only writer of one dense (n_cells, G) `.npy` file, filled in row blocks.
 

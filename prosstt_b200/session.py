@@ -80,11 +80,12 @@ class DensitySession(object):
     def step_to_host(self, seed, host_X, host_pt=None, host_codes=None, host_scal=None,
                      chunk_cells=None):
         """One pass streamed into host buffers (CPU tensors, ideally pinned).  Returns the
-        bytes copied device->host.  Synchronises before returning."""
+        bytes copied device->host.  Synchronises before returning.  host_X may be int32 or uint16
+        (narrow transfer format; the saturated elements are then in `self.engine.overflow`)."""
         self.index_and_scalings(seed)
         self.engine.draw_to_host(self.rows, self.s32, nat.derive_seed(seed, 2), self.first, host_X,
                                  chunk_cells=chunk_cells)
-        nbytes = host_X.numel() * 4
+        nbytes = host_X.numel() * host_X.element_size()
         for src, dst in ((self.pt, host_pt), (self.codes, host_codes), (self.s64, host_scal)):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)

@@ -961,3 +961,75 @@ def test_sampled_counts_to_csr_and_npy_shards(tmp_path):
                 w.append(Xr[lo:lo + 700])
         parts.append(np.load(path, mmap_mode="r"))
     assert np.array_equal(np.concatenate(parts, axis=0), X)
+
+
+def test_narrow_u16_kernel_and_overflow_list():
+    from prosstt_b200 import formats
+    dev = torch.device(DEV)
+    rng = np.random.RandomState(10)
+    for n, G, ldx, ldo in ((300, 404, 404, 404), (50, 21, 24, 32), (7, 1, 1, 1)):
+        Xh = rng.negative_binomial(0.7, 0.001, size=(n, ldx)).astype(np.int32)      # mean ~700
+        hot = rng.random_sample((n, ldx)) < 0.02
+        Xh[hot] = rng.choice([65534, 65535, 65536, 70000, 2000000000], size=int(hot.sum()))
+        X = torch.from_numpy(Xh).to(dev)
+        out = torch.full((n, ldo), 7, dtype=torch.uint16, device=dev)
+        cap = 4096
+        oi = torch.zeros(cap, dtype=torch.int64, device=dev)
+        ov = torch.zeros(cap, dtype=torch.int32, device=dev)
+        oc = torch.zeros(1, dtype=torch.int64, device=dev)
+        row0 = 1000
+        nat.call("pst_narrow_counts_u16", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, row0, oi, ov, cap, oc,
+                 nat.stream_ptr(dev))
+        got = out.cpu().numpy()
+        want = np.minimum(Xh[:, :G], 65535).astype(np.uint16)
+        assert np.array_equal(got[:, :G], want) and np.all(got[:, G:] == 7)
+        k = int(oc.item())
+        r, c = np.nonzero(Xh[:, :G] >= 65535)
+        assert k == len(r)
+        idx = oi[:k].cpu().numpy()
+        order = np.argsort(idx)
+        assert np.array_equal(idx[order], (r + row0) * G + c)
+        assert np.array_equal(ov[:k].cpu().numpy()[order], Xh[r, c])
+        # exact reconstruction
+        back = formats.widen_u16(got[:, :G].copy(), (idx[order] - row0 * G, ov[:k].cpu().numpy()[order]))
+        assert np.array_equal(back, Xh[:, :G])
+    # a list that is too small keeps counting and never writes past its capacity
+    oc.zero_()
+    small = torch.full((4,), -1, dtype=torch.int64, device=dev)
+    nat.call("pst_narrow_counts_u16", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, 0, small[:2], ov, 2, oc,
+             nat.stream_ptr(dev))
+    assert int(oc.item()) == k and small[2:].tolist() == [-1, -1]
+
+
+def test_uint16_host_output_is_lossless():
+    """sample_density into a uint16 host matrix + overflow list == the int32 result, including a
+    deep-sequencing run where thousands of counts exceed 65534."""
+    from prosstt_b200 import formats
+    t, alpha, beta = _bench_like_tree(2, 20, 6, 2000, seed=3)
+    n = 3000
+    for scale_mean in (0.0, 6.0):
+        kw = dict(alpha=alpha, beta=beta, seed=21, device=DEV, scale_mean=scale_mean)
+        X32 = sim.sample_density(t, n, dtype=np.int32, **kw)[0]
+        h16 = torch.empty((n, 2000), dtype=torch.uint16).pin_memory()
+        rest = (torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.int32), torch.empty(n, dtype=torch.float64))
+        ovf = {}
+        X16, pt, br, sc = sim.sample_density(t, n, host_out=(h16,) + rest + (ovf,), **kw)
+        assert X16.dtype == np.uint16
+        assert np.array_equal(formats.widen_u16(X16, ovf), X32)
+        n_big = int((X32 >= 65535).sum())
+        assert len(ovf["index"]) == n_big and np.all(np.diff(ovf["index"]) > 0)
+        if scale_mean == 0.0:
+            assert n_big == 0
+        else:
+            assert n_big > 100
+            with pytest.raises(OverflowError):               # no dict to receive them: loud
+                sim.sample_density(t, n, host_out=(h16,) + rest, **kw)
+    # 2-way partition: the shards' lists index into their own matrices
+    parts = []
+    for rank in range(2):
+        lo, hi = rank * n // 2, (rank + 1) * n // 2
+        h = torch.empty((hi - lo, 2000), dtype=torch.uint16)
+        o = {}
+        sim.sample_density(t, n, shard=(rank, 2), host_out=(h, rest[0][lo:hi], rest[1][lo:hi], rest[2][lo:hi], o), **kw)
+        parts.append(formats.widen_u16(h.numpy(), o))
+    assert np.array_equal(np.concatenate(parts), X32)

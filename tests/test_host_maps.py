@@ -236,3 +236,12 @@ def test_binary_formats_host_side(tmp_path):
     sp.save_npz(str(tmp_path / "c.npz"), m.tocsc())
     with pytest.raises(ValueError):
         formats.load_sparse_npz(str(tmp_path / "c.npz"))
+
+
+def test_widen_u16_host_side():
+    from prosstt_b200 import formats
+    X16 = np.array([[1, 65535, 3], [65535, 0, 65534]], dtype=np.uint16)
+    full = formats.widen_u16(X16, {"index": np.array([1, 3]), "value": np.array([65535, 123456], dtype=np.int32)})
+    assert full.dtype == np.int32 and full.tolist() == [[1, 65535, 3], [123456, 0, 65534]]
+    with pytest.raises(ValueError):
+        formats.widen_u16(X16, (np.array([1]), np.array([70000])))       # a saturated element is not listed
