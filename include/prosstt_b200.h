@@ -217,16 +217,16 @@ int pst_transform_counts(const int32_t *X, int64_t n, int64_t G, int64_t ldx, co
 int pst_csr_fill(const int32_t *X, int64_t n, int64_t G, int64_t ldx, const int64_t *indptr,
                  int32_t *indices, int32_t *data, uint32_t *flags, void *stream);
 
-/* uint16 transfer format for the device->host path (PCIe is the bound at 4 B per count):
- * out[i][g] = min(X[i][g], 65535).  Every element that reads 65535 also gets an entry in the
- * overflow list: ovf_index = (row0 + i)*G + g (flat index in the caller's full matrix),
- * ovf_value = the exact count, appended at atomicAdd(ovf_count, 1) when that slot is < ovf_cap.
- * ovf_count keeps counting past ovf_cap, so the caller can detect a list that was too small.
- * Entry order is not deterministic; sort by index.  (The reference returns int64;
- * simulation.py:651.) */
-int pst_narrow_counts_u16(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint16_t *out, int64_t ldo,
-                          int64_t row0, int64_t *ovf_index, int32_t *ovf_value, int64_t ovf_cap,
-                          uint64_t *ovf_count, void *stream);
+/* Narrow transfer formats for the device->host path (PCIe is the bound at 4 B per count):
+ * out[i][g] = min(X[i][g], SAT) as uint8 (out_bits 8, SAT 255) or uint16 (out_bits 16, SAT 65535),
+ * row stride ldo elements.  Every element that reads SAT also gets an entry in the overflow
+ * list: ovf_index = (row0 + i)*G + g (flat index in the caller's full matrix), ovf_value = the
+ * exact count, appended at atomicAdd(ovf_count, 1) when that slot is < ovf_cap.  ovf_count keeps
+ * counting past ovf_cap, so the caller can detect a list that was too small.  Entry order is
+ * not deterministic; sort by index.  (The reference returns int64; simulation.py:651.) */
+int pst_narrow_counts(const int32_t *X, int64_t n, int64_t G, int64_t ldx, void *out, int64_t ldo,
+                      int32_t out_bits, int64_t row0, int64_t *ovf_index, int32_t *ovf_value,
+                      int64_t ovf_cap, uint64_t *ovf_count, void *stream);
 
 #pragma GCC visibility pop
 #endif

@@ -48,7 +48,7 @@ _SIGNATURES = {
     "pst_count_stats": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "pst_transform_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p]),
     "pst_csr_fill": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
-    "pst_narrow_counts_u16": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "pst_narrow_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p]),
 }
 
 _lib = None

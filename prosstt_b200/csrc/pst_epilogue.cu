@@ -98,20 +98,22 @@ csr_fill_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx
 }
 
 // ---------------------------------------------------------------------------------------------
-// uint16 transfer format: out = min(X, 65535); every element that reads 65535 also has an entry
-// (flat index, exact value) in the overflow list, so the int32 matrix can be rebuilt exactly
+// narrow transfer formats: out = min(X, SAT) as uint8 (SAT = 255) or uint16 (SAT = 65535); every
+// element that reads SAT also has an entry (flat index, exact value) in the overflow list, so the
+// int32 matrix can be rebuilt exactly
 // ---------------------------------------------------------------------------------------------
-template <bool VEC>
+template <typename OUT, bool VEC>
 __global__ void __launch_bounds__(256)
-narrow_u16_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx,
-                  uint16_t *__restrict__ out, int64_t ldo, int64_t row0, int64_t *__restrict__ ovf_index,
-                  int32_t *__restrict__ ovf_value, int64_t ovf_cap, unsigned long long *__restrict__ ovf_count) {
+narrow_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx, OUT *__restrict__ out, int64_t ldo,
+              int64_t row0, int64_t *__restrict__ ovf_index, int32_t *__restrict__ ovf_value, int64_t ovf_cap,
+              unsigned long long *__restrict__ ovf_count) {
+  constexpr int SAT = (sizeof(OUT) == 1) ? 255 : 65535;
   const int64_t Q = (G + 3) / 4;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g0 = q * 4;
     for (int64_t row = blockIdx.y; row < n; row += gridDim.y) {
       const int32_t *src = X + row * ldx + g0;
-      uint16_t *dst = out + row * ldo + g0;
+      OUT *dst = out + row * ldo + g0;
       int v[4] = {0, 0, 0, 0};
       if (VEC) {
         const int4 w = __ldcs(reinterpret_cast<const int4 *>(src));
@@ -121,17 +123,22 @@ narrow_u16_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t l
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (v[j] >= 65535 && g0 + j < G) {                            // rare: one atomic per overflowing count
+        if (v[j] >= SAT && g0 + j < G) {                              // rare: one atomic per listed count
           const unsigned long long slot = atomicAdd(ovf_count, 1ull);
           if ((int64_t)slot < ovf_cap) { ovf_index[slot] = (row0 + row) * G + g0 + j; ovf_value[slot] = v[j]; }
-          v[j] = 65535;
+          v[j] = SAT;
         }
       }
       if (VEC) {
-        __stcs(reinterpret_cast<uint2 *>(dst), make_uint2((unsigned)v[0] | ((unsigned)v[1] << 16),
-                                                          (unsigned)v[2] | ((unsigned)v[3] << 16)));
+        if (sizeof(OUT) == 1) {
+          __stcs(reinterpret_cast<unsigned *>(dst),
+                 (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24));
+        } else {
+          __stcs(reinterpret_cast<uint2 *>(dst), make_uint2((unsigned)v[0] | ((unsigned)v[1] << 16),
+                                                            (unsigned)v[2] | ((unsigned)v[3] << 16)));
+        }
       } else {
-        for (int j = 0; j < 4 && g0 + j < G; ++j) dst[j] = (uint16_t)v[j];
+        for (int j = 0; j < 4 && g0 + j < G; ++j) dst[j] = (OUT)v[j];
       }
     }
   }
@@ -187,24 +194,27 @@ extern "C" int pst_csr_fill(const int32_t *X, int64_t n, int64_t G, int64_t ldx,
   return check_launch(fn);
 }
 
-extern "C" int pst_narrow_counts_u16(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint16_t *out, int64_t ldo,
-                                     int64_t row0, int64_t *ovf_index, int32_t *ovf_value, int64_t ovf_cap,
-                                     uint64_t *ovf_count, void *stream) {
-  const char *fn = "pst_narrow_counts_u16";
+extern "C" int pst_narrow_counts(const int32_t *X, int64_t n, int64_t G, int64_t ldx, void *out, int64_t ldo,
+                                 int32_t out_bits, int64_t row0, int64_t *ovf_index, int32_t *ovf_value,
+                                 int64_t ovf_cap, uint64_t *ovf_count, void *stream) {
+  const char *fn = "pst_narrow_counts";
   PST_REQUIRE(n >= 0 && G >= 0 && ldx >= G && ldo >= G && row0 >= 0 && ovf_cap >= 0, fn,
               "need n, G, row0, ovf_cap >= 0, ldx >= G and ldo >= G");
+  PST_REQUIRE(out_bits == 8 || out_bits == 16, fn, "out_bits must be 8 or 16");
   if (n == 0 || G == 0) return 0;
   PST_REQUIRE(X && out && ovf_count && (ovf_cap == 0 || (ovf_index && ovf_value)), fn, "null pointer");
+  const int64_t obytes = out_bits / 8;
   const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
-                   ((uintptr_t)out % 8 == 0);
+                   ((uintptr_t)out % (4 * obytes) == 0);
   const int64_t qblocks = std::min<int64_t>((((G + 3) / 4) + 255) / 256, 64);
   const int64_t yblocks = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)kNumSM * 16 + qblocks - 1) / qblocks));
   const dim3 grid((unsigned)qblocks, (unsigned)yblocks);
-  if (vec)
-    narrow_u16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, G, ldx, out, ldo, row0, ovf_index, ovf_value,
-                                                                    ovf_cap, (unsigned long long *)ovf_count);
-  else
-    narrow_u16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(X, n, G, ldx, out, ldo, row0, ovf_index, ovf_value,
-                                                                     ovf_cap, (unsigned long long *)ovf_count);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long *cnt = (unsigned long long *)ovf_count;
+#define PST_LAUNCH_NARROW(T, V) \
+  narrow_kernel<T, V><<<grid, 256, 0, st>>>(X, n, G, ldx, (T *)out, ldo, row0, ovf_index, ovf_value, ovf_cap, cnt)
+  if (out_bits == 8) { if (vec) PST_LAUNCH_NARROW(uint8_t, true); else PST_LAUNCH_NARROW(uint8_t, false); }
+  else { if (vec) PST_LAUNCH_NARROW(uint16_t, true); else PST_LAUNCH_NARROW(uint16_t, false); }
+#undef PST_LAUNCH_NARROW
   return check_launch(fn);
 }

@@ -211,19 +211,24 @@ class CountEngine(object):
                  nat.ptr(self.flags), self.sampler, order, st)
         return out
 
-    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=1 << 20):
+    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=None):
         """Sample in cell chunks and stream them into `host_out` (an (n, G) CPU tensor, ideally
         pinned): sampling of chunk i+1 overlaps the copy of chunk i.
 
         host_out.dtype int32: the counts as sampled (4 B per count over PCIe).
-        host_out.dtype uint16: the narrow transfer format (2 B per count): min(count, 65535), and
-        every element that reads 65535 is listed exactly in `self.overflow` = (flat index into
-        host_out, int32 value) NumPy arrays sorted by index (formats.widen_u16 rebuilds int32)."""
+        host_out.dtype uint16 / uint8: the narrow transfer formats (2 / 1 B per count):
+        min(count, SAT) with SAT = 65535 / 255, and every element that reads SAT is listed exactly
+        in `self.overflow` = (flat index into host_out, int32 value) NumPy arrays sorted by index
+        (formats.widen rebuilds int32).  At default depth about 2 in 10^4 counts reach 255 and none
+        reaches 65535."""
         n = int(rows.numel())
-        narrow = host_out.dtype == torch.uint16
+        narrow = host_out.dtype in (torch.uint16, torch.uint8)
         if not narrow and host_out.dtype != torch.int32:
-            raise ValueError("host_out must be an int32 or uint16 CPU tensor")
-        width = 2 if narrow else 4
+            raise ValueError("host_out must be an int32, uint16 or uint8 CPU tensor")
+        width = host_out.element_size()
+        if narrow and overflow_cap is None:
+            # uint8 lists every count >= 255 (2e-4 of them at default depth; allow 50x that)
+            overflow_cap = (1 << 20) if width == 2 else max(1 << 20, n * self.G // 100)
         if chunk_cells is None:
             # ~1 GiB copies keep the copy engine at its large-transfer rate; the first chunks are
             # smaller so that the device->host stream starts almost immediately
@@ -254,8 +259,8 @@ class CountEngine(object):
                 main.wait_event(free[i & 1])
             if narrow:
                 self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=work[:hi - lo])
-                nat.call("pst_narrow_counts_u16", work.data_ptr(), hi - lo, self.G, self.G, buf.data_ptr(), self.G,
-                         lo, ovf_index, ovf_value, int(overflow_cap), ovf_count, nat.stream_ptr(self.dev))
+                nat.call("pst_narrow_counts", work.data_ptr(), hi - lo, self.G, self.G, buf.data_ptr(), self.G,
+                         8 * width, lo, ovf_index, ovf_value, int(overflow_cap), ovf_count, nat.stream_ptr(self.dev))
             else:
                 self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=buf)
             done = torch.cuda.Event()
@@ -268,12 +273,11 @@ class CountEngine(object):
         if narrow:
             count = int(ovf_count.item())
             if count > overflow_cap:
-                raise OverflowError("%d counts exceed 65534 but the overflow list holds %d: use an int32 "
-                                    "host buffer or a larger overflow_cap" % (count, overflow_cap))
-            index = ovf_index[:count].cpu().numpy()
-            value = ovf_value[:count].cpu().numpy()
-            order = np.argsort(index, kind="stable")
-            self.overflow = (index[order], value[order])
+                raise OverflowError("%d counts reach the saturation value of %s but the overflow list holds %d: "
+                                    "use a wider host buffer or a larger overflow_cap"
+                                    % (count, str(host_out.dtype).replace("torch.", ""), overflow_cap))
+            index, order = torch.sort(ovf_index[:count])            # appended in no particular order
+            self.overflow = (index.cpu().numpy(), ovf_value[:count][order].cpu().numpy())
         return host_out
 
     def check(self):

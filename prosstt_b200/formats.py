@@ -79,16 +79,18 @@ def csr_to_dense(indptr, indices, data, shape):
     return out
 
 
-def widen_u16(X16, overflow):
-    """Exact int32 matrix from the uint16 transfer format: X16 (n, G) uint16 with saturated
-    elements reading 65535, overflow = (flat index, value) arrays or the dict filled by
+def widen(Xn, overflow):
+    """Exact int32 matrix from a narrow transfer format: Xn (n, G) uint8 or uint16 with saturated
+    elements reading 255 / 65535, overflow = (flat index, value) arrays or the dict filled by
     `sample_density(host_out=(..., dict))`."""
     if isinstance(overflow, dict):
         overflow = (overflow["index"], overflow["value"])
-    X16 = np.asarray(X16)
-    out = X16.astype(np.int32)
+    Xn = np.asarray(Xn)
+    if Xn.dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+        raise TypeError("expected a uint8 or uint16 matrix")
+    out = Xn.astype(np.int32)
     index, value = np.asarray(overflow[0]), np.asarray(overflow[1])
-    saturated = np.flatnonzero(X16.reshape(-1) == 65535)
+    saturated = np.flatnonzero(Xn.reshape(-1) == np.iinfo(Xn.dtype).max)
     if not np.array_equal(saturated, index):
         raise ValueError("overflow list does not match the saturated elements of the matrix")
     out.reshape(-1)[index] = value

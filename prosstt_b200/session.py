@@ -80,8 +80,8 @@ class DensitySession(object):
     def step_to_host(self, seed, host_X, host_pt=None, host_codes=None, host_scal=None,
                      chunk_cells=None):
         """One pass streamed into host buffers (CPU tensors, ideally pinned).  Returns the
-        bytes copied device->host.  Synchronises before returning.  host_X may be int32 or uint16
-        (narrow transfer format; the saturated elements are then in `self.engine.overflow`)."""
+        bytes copied device->host.  Synchronises before returning.  host_X may be int32, uint16 or
+        uint8 (narrow transfer formats; the saturated elements are then in `self.engine.overflow`)."""
         self.index_and_scalings(seed)
         self.engine.draw_to_host(self.rows, self.s32, nat.derive_seed(seed, 2), self.first, host_X,
                                  chunk_cells=chunk_cells)

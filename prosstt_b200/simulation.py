@@ -315,10 +315,10 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
     host_out = (X, pseudotime, branch_codes, scalings) preallocated CPU tensors (int32 (n,G),
     int64, int32, float64; ideally pinned): the counts are streamed into them in cell chunks
     while the next chunk is being sampled, and numpy views of them are returned.  X may also be
-    uint16 (half the PCIe bytes): elements read min(count, 65535) and a fifth entry of host_out,
-    a dict, receives the exact values of the saturated elements as "index" (flat, into X) and
-    "value" arrays (formats.widen_u16 rebuilds the int32 matrix); without the dict an overflow
-    raises OverflowError instead of passing silently."""
+    uint16 or uint8 (a half / a quarter of the PCIe bytes): elements read min(count, 65535 / 255)
+    and a fifth entry of host_out, a dict, receives the exact values of the saturated elements as
+    "index" (flat, into X) and "value" arrays (formats.widen rebuilds the int32 matrix); without
+    the dict a saturated element raises OverflowError instead of passing silently."""
     n = int(rows.numel())
     s64, s32 = sut.calc_scalings(n, scale, scale_mean, scale_v, seed=nat.derive_seed(seed, 1),
                                  first=first, device=dev, return_device=True)
@@ -326,8 +326,9 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
     if host_out is not None:
         hX, hpt, hcodes, hs = host_out[:4]
         overflow = host_out[4] if len(host_out) > 4 else None
-        if tuple(hX.shape) != (n, engine.G) or hX.dtype not in (torch.int32, torch.uint16):
-            raise ValueError("host_out[0] must be an int32 (or uint16) CPU tensor of shape (%d, %d)" % (n, engine.G))
+        if tuple(hX.shape) != (n, engine.G) or hX.dtype not in (torch.int32, torch.uint16, torch.uint8):
+            raise ValueError("host_out[0] must be an int32 (or uint16 / uint8) CPU tensor of shape (%d, %d)"
+                             % (n, engine.G))
         hpt.copy_(pt, non_blocking=True)
         hcodes.copy_(codes, non_blocking=True)
         hs.copy_(s64, non_blocking=True)
@@ -338,8 +339,9 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
             if overflow is not None:
                 overflow["index"], overflow["value"] = engine.overflow
             elif len(engine.overflow[0]):
-                raise OverflowError("%d counts exceed 65534: pass a dict as host_out[4] to receive them, or use "
-                                    "an int32 buffer" % len(engine.overflow[0]))
+                raise OverflowError("%d counts saturate the %s matrix: pass a dict as host_out[4] to receive them, "
+                                    "or use an int32 buffer"
+                                    % (len(engine.overflow[0]), str(hX.dtype).replace("torch.", "")))
         return hX.numpy(), hpt.numpy(), tables.branch_names(hcodes.numpy()), hs.numpy()
     X = engine.draw(rows, s32, nat.derive_seed(seed, 2), first)
     return _finish(engine, tables, X, pt, codes, s64, dtype, out)

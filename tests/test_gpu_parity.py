@@ -963,73 +963,87 @@ def test_sampled_counts_to_csr_and_npy_shards(tmp_path):
     assert np.array_equal(np.concatenate(parts, axis=0), X)
 
 
-def test_narrow_u16_kernel_and_overflow_list():
+@pytest.mark.parametrize("bits", [8, 16])
+def test_narrow_kernel_and_overflow_list(bits):
     from prosstt_b200 import formats
     dev = torch.device(DEV)
     rng = np.random.RandomState(10)
-    for n, G, ldx, ldo in ((300, 404, 404, 404), (50, 21, 24, 32), (7, 1, 1, 1)):
-        Xh = rng.negative_binomial(0.7, 0.001, size=(n, ldx)).astype(np.int32)      # mean ~700
+    sat = (1 << bits) - 1
+    tdt = torch.uint8 if bits == 8 else torch.uint16
+    for n, G, ldx, ldo in ((7, 1, 1, 4), (50, 21, 24, 32), (300, 404, 404, 404)):
+        Xh = rng.negative_binomial(0.7, 0.7 / (0.7 + sat / 90.0), size=(n, ldx)).astype(np.int32)   # mean ~ sat/90
         hot = rng.random_sample((n, ldx)) < 0.02
-        Xh[hot] = rng.choice([65534, 65535, 65536, 70000, 2000000000], size=int(hot.sum()))
+        Xh[hot] = rng.choice([sat - 1, sat, sat + 1, 70000, 2000000000], size=int(hot.sum()))
         X = torch.from_numpy(Xh).to(dev)
-        out = torch.full((n, ldo), 7, dtype=torch.uint16, device=dev)
-        cap = 4096
+        out = torch.full((n, ldo), 7, dtype=tdt, device=dev)
+        cap = 8192
         oi = torch.zeros(cap, dtype=torch.int64, device=dev)
         ov = torch.zeros(cap, dtype=torch.int32, device=dev)
         oc = torch.zeros(1, dtype=torch.int64, device=dev)
         row0 = 1000
-        nat.call("pst_narrow_counts_u16", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, row0, oi, ov, cap, oc,
+        nat.call("pst_narrow_counts", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, bits, row0, oi, ov, cap, oc,
                  nat.stream_ptr(dev))
         got = out.cpu().numpy()
-        want = np.minimum(Xh[:, :G], 65535).astype(np.uint16)
+        want = np.minimum(Xh[:, :G], sat).astype(got.dtype)
         assert np.array_equal(got[:, :G], want) and np.all(got[:, G:] == 7)
         k = int(oc.item())
-        r, c = np.nonzero(Xh[:, :G] >= 65535)
-        assert k == len(r)
+        r, c = np.nonzero(Xh[:, :G] >= sat)
+        assert k == len(r) and k <= cap and (k > 0 or n < 300)
         idx = oi[:k].cpu().numpy()
         order = np.argsort(idx)
         assert np.array_equal(idx[order], (r + row0) * G + c)
         assert np.array_equal(ov[:k].cpu().numpy()[order], Xh[r, c])
         # exact reconstruction
-        back = formats.widen_u16(got[:, :G].copy(), (idx[order] - row0 * G, ov[:k].cpu().numpy()[order]))
+        back = formats.widen(got[:, :G].copy(), (idx[order] - row0 * G, ov[:k].cpu().numpy()[order]))
         assert np.array_equal(back, Xh[:, :G])
     # a list that is too small keeps counting and never writes past its capacity
     oc.zero_()
     small = torch.full((4,), -1, dtype=torch.int64, device=dev)
-    nat.call("pst_narrow_counts_u16", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, 0, small[:2], ov, 2, oc,
+    nat.call("pst_narrow_counts", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, bits, 0, small[:1], ov, 1, oc,
              nat.stream_ptr(dev))
-    assert int(oc.item()) == k and small[2:].tolist() == [-1, -1]
+    assert int(oc.item()) == k and small[1:].tolist() == [-1, -1, -1]
+    with pytest.raises(ValueError):
+        nat.call("pst_narrow_counts", X.data_ptr(), n, G, ldx, out.data_ptr(), ldo, 12, 0, oi, ov, cap, oc,
+                 nat.stream_ptr(dev))
 
 
-def test_uint16_host_output_is_lossless():
-    """sample_density into a uint16 host matrix + overflow list == the int32 result, including a
-    deep-sequencing run where thousands of counts exceed 65534."""
+@pytest.mark.parametrize("tdt", [torch.uint16, torch.uint8])
+def test_narrow_host_output_is_lossless(tdt):
+    """sample_density into a uint16 / uint8 host matrix + overflow list == the int32 result,
+    including a deep-sequencing run where thousands of counts exceed 65534."""
     from prosstt_b200 import formats
     t, alpha, beta = _bench_like_tree(2, 20, 6, 2000, seed=3)
     n = 3000
+    sat = 65535 if tdt == torch.uint16 else 255
     for scale_mean in (0.0, 6.0):
         kw = dict(alpha=alpha, beta=beta, seed=21, device=DEV, scale_mean=scale_mean)
         X32 = sim.sample_density(t, n, dtype=np.int32, **kw)[0]
-        h16 = torch.empty((n, 2000), dtype=torch.uint16).pin_memory()
+        hn = torch.empty((n, 2000), dtype=tdt).pin_memory()
         rest = (torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.int32), torch.empty(n, dtype=torch.float64))
         ovf = {}
-        X16, pt, br, sc = sim.sample_density(t, n, host_out=(h16,) + rest + (ovf,), **kw)
-        assert X16.dtype == np.uint16
-        assert np.array_equal(formats.widen_u16(X16, ovf), X32)
-        n_big = int((X32 >= 65535).sum())
+        if tdt == torch.uint8 and scale_mean == 6.0:
+            with pytest.raises(OverflowError):               # most counts saturate: the list overflows, loudly
+                sim.sample_density(t, n, host_out=(hn,) + rest + (ovf,), **kw)
+            continue
+        Xn, pt, br, sc = sim.sample_density(t, n, host_out=(hn,) + rest + (ovf,), **kw)
+        assert Xn.dtype == hn.numpy().dtype
+        assert np.array_equal(formats.widen(Xn, ovf), X32)
+        n_big = int((X32 >= sat).sum())
         assert len(ovf["index"]) == n_big and np.all(np.diff(ovf["index"]) > 0)
-        if scale_mean == 0.0:
+        if scale_mean == 0.0 and tdt == torch.uint16:
             assert n_big == 0
         else:
             assert n_big > 100
             with pytest.raises(OverflowError):               # no dict to receive them: loud
-                sim.sample_density(t, n, host_out=(h16,) + rest, **kw)
+                sim.sample_density(t, n, host_out=(hn,) + rest, **kw)
     # 2-way partition: the shards' lists index into their own matrices
+    kw["scale_mean"] = 0.0 if tdt == torch.uint8 else 6.0
+    X32 = sim.sample_density(t, n, dtype=np.int32, **kw)[0]
     parts = []
     for rank in range(2):
         lo, hi = rank * n // 2, (rank + 1) * n // 2
-        h = torch.empty((hi - lo, 2000), dtype=torch.uint16)
+        h = torch.empty((hi - lo, 2000), dtype=tdt)
         o = {}
         sim.sample_density(t, n, shard=(rank, 2), host_out=(h, rest[0][lo:hi], rest[1][lo:hi], rest[2][lo:hi], o), **kw)
-        parts.append(formats.widen_u16(h.numpy(), o))
+        parts.append(formats.widen(h.numpy(), o))
     assert np.array_equal(np.concatenate(parts), X32)

@@ -238,10 +238,14 @@ def test_binary_formats_host_side(tmp_path):
         formats.load_sparse_npz(str(tmp_path / "c.npz"))
 
 
-def test_widen_u16_host_side():
+def test_widen_host_side():
     from prosstt_b200 import formats
     X16 = np.array([[1, 65535, 3], [65535, 0, 65534]], dtype=np.uint16)
-    full = formats.widen_u16(X16, {"index": np.array([1, 3]), "value": np.array([65535, 123456], dtype=np.int32)})
+    full = formats.widen(X16, {"index": np.array([1, 3]), "value": np.array([65535, 123456], dtype=np.int32)})
     assert full.dtype == np.int32 and full.tolist() == [[1, 65535, 3], [123456, 0, 65534]]
+    X8 = np.array([[255, 254], [0, 255]], dtype=np.uint8)
+    assert formats.widen(X8, (np.array([0, 3]), np.array([255, 1000], dtype=np.int32))).tolist() == [[255, 254], [0, 1000]]
     with pytest.raises(ValueError):
-        formats.widen_u16(X16, (np.array([1]), np.array([70000])))       # a saturated element is not listed
+        formats.widen(X16, (np.array([1]), np.array([70000])))          # a saturated element is not listed
+    with pytest.raises(TypeError):
+        formats.widen(X16.astype(np.int16), (np.array([], dtype=np.int64), np.array([], dtype=np.int32)))
