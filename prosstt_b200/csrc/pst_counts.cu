@@ -198,11 +198,11 @@ constexpr int HY_CHUNK_CELLS = 64;           // cells per chunk (x 32 quads = 81
 
 template <int KFIX, bool VEC, bool ALL_MIX>
 __global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
-draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, int64_t P,
-                          int64_t G, uint32_t Q, const int32_t *__restrict__ row_of_cell,
+draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, uint32_t P,
+                          uint32_t G, uint32_t Q, const int32_t *__restrict__ row_of_cell,
                           const float *__restrict__ scaling, const float *__restrict__ alpha,
                           const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
-                          int32_t *__restrict__ X, int64_t ldx, uint32_t *__restrict__ flags,
+                          int32_t *__restrict__ X, uint32_t ldx, uint32_t *__restrict__ flags,
                           const int32_t *__restrict__ cell_order, float mu_max, float var_max) {
   __shared__ HyWarpQueues queues[HY_WARPS];
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
@@ -251,7 +251,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     }
     if (act) {
       const int2 w = wq.sw[e];
-      X[(int64_t)w.x * ldx + w.y] = cn;
+      X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
     }
   };
   // one mixture step for up to 32 queued entries; rejected entries go back to the queue (returns
@@ -278,7 +278,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       if (status == MIX_DONE) {
         int val = (int)value;
         if (value > 2147483520.f) { val = 2147483647; flag |= PST_FLAG_CLAMPED; }
-        X[(int64_t)ccell * ldx + gene] = val;
+        X[(uint64_t)(uint32_t)ccell * ldx + (uint32_t)gene] = val;
       }
     }
     const bool again = act && status != MIX_DONE;
@@ -302,13 +302,13 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   // cells are visited in `cell_order` (grouped by tree row so that concurrently running warps
   // share means rows in L2/L1); results do not depend on the order
   auto load_means = [&](int32_t row, uint32_t g0) -> float4 {
-    const int32_t r = ((uint32_t)row < (uint64_t)P) ? row : 0;       // bad rows are flagged at use
+    const int32_t r = ((uint32_t)row < P) ? row : 0;       // bad rows are flagged at use
     if constexpr (VEC) {
-      return ldg_f4_hint(means + (int64_t)r * G + g0, keep);
+      return ldg_f4_hint(means + ((uint64_t)(uint32_t)r * G + g0), keep);
     } else {
       float m[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] = ((int64_t)g0 + j < G) ? means[(int64_t)r * G + g0 + j] : 1.f;
+      for (int j = 0; j < 4; ++j) m[j] = (g0 + j < G) ? means[(uint64_t)(uint32_t)r * G + g0 + j] : 1.f;
       return make_float4(m[0], m[1], m[2], m[3]);
     }
   };
@@ -337,7 +337,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool ok = (int64_t)g0 + j < G;
+        const bool ok = g0 + j < G;
         al[j] = ok ? alpha[g0 + j] : 0.f;
         bm[j] = ok ? beta_m1[g0 + j] : 1.f;
       }
@@ -356,8 +356,8 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       meta_s = scaling[meta_cell];
     };
     auto stage_means = [&](int32_t r) {
-      const int32_t rr = ((uint32_t)r < (uint64_t)P) ? r : 0;
-      cp_async16(&wq.mstage[lane], means + (int64_t)rr * G + g0, keep);
+      const int32_t rr = ((uint32_t)r < P) ? r : 0;
+      cp_async16(&wq.mstage[lane], means + ((uint64_t)(uint32_t)rr * G + g0), keep);
       cp_async_commit();
     };
     load_meta(0);
@@ -375,7 +375,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       else mnext = load_means(row1, g0);
 
       // ---- this cell's quad
-      const bool row_ok = (uint32_t)row < (uint64_t)P;
+      const bool row_ok = (uint32_t)row < P;
       if (!row_ok) flag |= PST_FLAG_ROW;
       const bool live = lane_ok && row_ok;
       const float m[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
@@ -425,10 +425,12 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
       }
       }  // !ALL_MIX
-      // large means: queue them for the mixture now, so mu/theta are dead during the head
+      // large means: queue them for the mixture now, so mu/theta are dead during the head.  Many
+      // (cell, strip) pairs have none: one vote skips the four ballots
+      if (ALL_MIX || __any_sync(0xffffffffu, live && !(small[0] && small[1] && small[2] && small[3]))) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool to_mix = live && !small[j] && (VEC || (int64_t)g0 + j < G);
+        const bool to_mix = live && !small[j] && (VEC || g0 + j < G);
         const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
         if (to_mix) {
           const int e = ng + __popc(mg & lt_mask);
@@ -436,6 +438,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
           wq.ga[e] = 0;
         }
         ng += __popc(mg);
+      }
       }
       // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
       if constexpr (!ALL_MIX) {
@@ -453,19 +456,19 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       int out[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool in_range = live && (VEC || (int64_t)g0 + j < G);
+        const bool in_range = live && (VEC || g0 + j < G);
         to_search[j] = in_range && small[j] && (d[j] < 0.f);
         out[j] = (small[j] && !(d[j] < 0.f)) ? cnt[j] : 0;
       }
       // store the quad (undecided / mixture slots hold 0 until their queue is drained)
       if (lane_ok) {
-        int32_t *dst = X + (int64_t)cell * ldx + g0;
+        int32_t *dst = X + ((uint64_t)(uint32_t)cell * ldx + g0);
         if (VEC) {
           *reinterpret_cast<int4 *>(dst) = make_int4(out[0], out[1], out[2], out[3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if ((int64_t)g0 + j < G) dst[j] = out[j];
+            if (g0 + j < G) dst[j] = out[j];
         }
       }
       // enqueue the undecided inversions (all lanes take part in the ballots)
@@ -706,7 +709,8 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const char *fn = "pst_draw_counts";
   PST_REQUIRE(P >= 0 && G >= 0 && n >= 0 && cell0 >= 0, fn, "negative size");
   PST_REQUIRE(ldx >= G, fn, "ldx < G");
-  PST_REQUIRE(G < (int64_t)1 << 31, fn, "G must be below 2^31");
+  PST_REQUIRE(G < (int64_t)1 << 31 && P < (int64_t)1 << 31 && ldx < (int64_t)1 << 32, fn,
+              "G and P must be below 2^31 and ldx below 2^32");
   PST_REQUIRE(n < (int64_t)1 << 31, fn, "at most 2^31-1 cells per call (shard or chunk the cells)");
   PST_REQUIRE(cell0 + n < (int64_t)1 << 48, fn, "cell index must be below 2^48");
   PST_REQUIRE(sampler == PST_SAMPLER_GAMMA_POISSON || sampler == PST_SAMPLER_HYBRID, fn, "unknown sampler");
@@ -739,11 +743,11 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
 #define PST_LAUNCH_HYBRID(KF, MIX)                                                                         \
     do {                                                                                                   \
       if (vec) draw_counts_hybrid_kernel<KF, true, MIX><<<hb, HY_THREADS, 0, st>>>(                        \
-          PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
-          ldx, flags, cell_order, mu_max, var_max);                                                        \
+          PhiloxKey(seed), means, (uint32_t)P, (uint32_t)G, (uint32_t)Q, row_of_cell, scaling, alpha,      \
+          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max);                        \
       else draw_counts_hybrid_kernel<KF, false, MIX><<<hb, HY_THREADS, 0, st>>>(                           \
-          PhiloxKey(seed), means, P, G, (uint32_t)Q, row_of_cell, scaling, alpha, beta_m1, cell0, n, X,    \
-          ldx, flags, cell_order, mu_max, var_max);                                                        \
+          PhiloxKey(seed), means, (uint32_t)P, (uint32_t)G, (uint32_t)Q, row_of_cell, scaling, alpha,      \
+          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max);                        \
     } while (0)
     if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
       PST_LAUNCH_HYBRID(HY_KFIX, true);
