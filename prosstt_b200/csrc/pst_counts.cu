@@ -203,7 +203,12 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
                           const float *__restrict__ scaling, const float *__restrict__ alpha,
                           const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
                           int32_t *__restrict__ X, uint32_t ldx, uint32_t *__restrict__ flags,
-                          const int32_t *__restrict__ cell_order, float mu_max, float var_max) {
+                          const int32_t *__restrict__ cell_order, float mu_max_arg, float var_max_arg) {
+#ifdef PST_DEV_KNOBS
+  const float mu_max = mu_max_arg, var_max = var_max_arg;
+#else
+  constexpr float mu_max = HY_MU_MAX, var_max = HY_VAR_MAX;      // immediates in the route test
+#endif
   __shared__ HyWarpQueues queues[HY_WARPS];
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -322,9 +327,10 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     if ((int64_t)claimed >= n_chunks) break;                  // no work left
     const uint32_t cgroup = claimed / n_strips;
     const uint32_t strip = claimed - cgroup * n_strips;
-    const uint32_t quad = strip * 32u + (uint32_t)lane;
-    const bool lane_ok = quad < Q;
-    const uint32_t g0 = (lane_ok ? quad : 0u) * 4u;
+    // lanes past the last quad of the last strip repeat quad Q-1: same key, same counts, same
+    // addresses, so the duplicates are harmless and no per-count "lane is live" predicate is needed
+    const uint32_t quad = min(strip * 32u + (uint32_t)lane, Q - 1u);
+    const uint32_t g0 = quad * 4u;
     const int64_t cell_lo = (int64_t)cgroup * HY_CHUNK_CELLS;
     const int n_cells = (int)((n - cell_lo) < HY_CHUNK_CELLS ? (n - cell_lo) : HY_CHUNK_CELLS);
     // per-gene parameters of this lane's quad, once per chunk
@@ -375,9 +381,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       else mnext = load_means(row1, g0);
 
       // ---- this cell's quad
-      const bool row_ok = (uint32_t)row < P;
-      if (!row_ok) flag |= PST_FLAG_ROW;
-      const bool live = lane_ok && row_ok;
+      if (!((uint32_t)row < P)) flag |= PST_FLAG_ROW;        // sampled from row 0; the caller raises
       const float m[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
       float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
       int cnt[4];
@@ -427,10 +431,10 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       }  // !ALL_MIX
       // large means: queue them for the mixture now, so mu/theta are dead during the head.  Many
       // (cell, strip) pairs have none: one vote skips the four ballots
-      if (ALL_MIX || __any_sync(0xffffffffu, live && !(small[0] && small[1] && small[2] && small[3]))) {
+      if (ALL_MIX || __any_sync(0xffffffffu, !(small[0] && small[1] && small[2] && small[3]))) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool to_mix = live && !small[j] && (VEC || g0 + j < G);
+        const bool to_mix = !small[j] && (VEC || g0 + j < G);
         const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
         if (to_mix) {
           const int e = ng + __popc(mg & lt_mask);
@@ -456,12 +460,12 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       int out[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool in_range = live && (VEC || g0 + j < G);
-        to_search[j] = in_range && small[j] && (d[j] < 0.f);
-        out[j] = (small[j] && !(d[j] < 0.f)) ? cnt[j] : 0;
+        to_search[j] = (VEC || g0 + j < G) && small[j] && (d[j] < 0.f);
+        out[j] = small[j] ? cnt[j] : 0;
       }
-      // store the quad (undecided / mixture slots hold 0 until their queue is drained)
-      if (lane_ok) {
+      // store the quad: undecided slots hold KFIX and mixture slots 0 until their queue entry is
+      // drained (the __syncwarp below orders this store before the drain's)
+      {
         int32_t *dst = X + ((uint64_t)(uint32_t)cell * ldx + g0);
         if (VEC) {
           *reinterpret_cast<int4 *>(dst) = make_int4(out[0], out[1], out[2], out[3]);
