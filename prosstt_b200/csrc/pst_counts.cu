@@ -227,7 +227,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     const bool act = lane < cnt;
     const int e = first + lane;
     const float4 st = act ? wq.se[e] : make_float4(0.f, 1.f, 0.f, 0.f);
-    float pp = st.x, dd = st.y;
+    float pp = st.x * inv_fact[KFIX - 1], dd = st.y;       // back to P(KFIX-1)
     const float aa = st.z, qq = st.w;
     int cn = KFIX;
     // second stage: HY_STAGE2 further terms unrolled with compile-time k (4-5 instructions per
@@ -306,8 +306,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   const uint32_t n_strips = (Q + 31u) / 32u;
   // cells are visited in `cell_order` (grouped by tree row so that concurrently running warps
   // share means rows in L2/L1); results do not depend on the order
-  auto load_means = [&](int32_t row, uint32_t g0) -> float4 {
-    const int32_t r = ((uint32_t)row < P) ? row : 0;       // bad rows are flagged at use
+  auto load_means = [&](int32_t r, uint32_t g0) -> float4 {       // r validated in load_meta
     if constexpr (VEC) {
       return ldg_f4_hint(means + ((uint64_t)(uint32_t)r * G + g0), keep);
     } else {
@@ -360,10 +359,12 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       meta_cell = cell_order ? cell_order[pos] : (int32_t)pos;
       meta_row = row_of_cell[meta_cell];
       meta_s = scaling[meta_cell];
+      // rows are validated here, once per cell: a bad row is flagged (the caller raises) and
+      // sampled from row 0 so that every address below stays in range
+      if (!((uint32_t)meta_row < P)) { flag |= PST_FLAG_ROW; meta_row = 0; }
     };
     auto stage_means = [&](int32_t r) {
-      const int32_t rr = ((uint32_t)r < P) ? r : 0;
-      cp_async16(&wq.mstage[lane], means + ((uint64_t)(uint32_t)rr * G + g0), keep);
+      cp_async16(&wq.mstage[lane], means + ((uint64_t)(uint32_t)r * G + g0), keep);
       cp_async_commit();
     };
     load_meta(0);
@@ -381,7 +382,6 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       else mnext = load_means(row1, g0);
 
       // ---- this cell's quad
-      if (!((uint32_t)row < P)) flag |= PST_FLAG_ROW;        // sampled from row 0; the caller raises
       const float m[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
       float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
       int cnt[4];
@@ -481,7 +481,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         const unsigned ms = __ballot_sync(0xffffffffu, to_search[j]);
         if (to_search[j]) {
           const int e = ns + __popc(ms & lt_mask);
-          wq.se[e] = make_float4(t[j] * inv_fact[KFIX - 1], d[j], a[j], q[j]);   // back to P(KFIX-1)
+          wq.se[e] = make_float4(t[j], d[j], a[j], q[j]);     // t = P(KFIX-1) (KFIX-1)!, rescaled in the drain
           wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
         }
         ns += __popc(ms);
