@@ -75,6 +75,11 @@ __device__ __forceinline__ uint4 philox_s(uint32_t k0, uint32_t k1, uint32_t c0,
 __device__ __forceinline__ float u01(uint32_t w) {
   return fminf(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
 }
+// the same without the clamp: (0,1], and 1.0 only for the top 128 values of w (3e-8).  For the
+// cdf inversion, whose search stops where the fp32 cdf freezes, u = 1 is just the extreme quantile
+__device__ __forceinline__ float u01_closed_top(uint32_t w) {
+  return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
 // 53-bit double in [0,1) exactly as numpy's legacy random_sample builds it
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);

@@ -185,11 +185,19 @@ struct HyWarpQueues {
   float4 mstage[32];        // next cell's means quad, filled by cp.async (one slot per lane)
 };
 
-// 1/k!, k = 0..16 (immediates after unrolling)
-#define PST_INV_FACT_TABLE {1.0f, 1.0f, 0.5f, 1.0f / 6, 1.0f / 24, 1.0f / 120, 1.0f / 720, 1.0f / 5040,        \
-                            1.0f / 40320, 1.0f / 362880, 1.0f / 3628800, 1.0f / 39916800, 1.0f / 479001600,     \
-                            1.0f / 6227020800.0f, 1.0f / 87178291200.0f, 1.0f / 1307674368000.0f,               \
-                            1.0f / 20922789888000.0f}
+// 1/k! and k!, k = 0..33 (immediates after unrolling; 1/33! = 1.15e-37 is the last normal fp32 value of the series)
+#define PST_INV_FACT_TABLE {1.000000000e+00f, 1.000000000e+00f, 5.000000000e-01f, 1.666666667e-01f,               \
+    4.166666667e-02f, 8.333333333e-03f, 1.388888889e-03f, 1.984126984e-04f, 2.480158730e-05f, 2.755731922e-06f,   \
+    2.755731922e-07f, 2.505210839e-08f, 2.087675699e-09f, 1.605904384e-10f, 1.147074560e-11f, 7.647163732e-13f,   \
+    4.779477332e-14f, 2.811457254e-15f, 1.561920697e-16f, 8.220635247e-18f, 4.110317623e-19f, 1.957294106e-20f,   \
+    8.896791392e-22f, 3.868170171e-23f, 1.611737571e-24f, 6.446950284e-26f, 2.479596263e-27f, 9.183689864e-29f,   \
+    3.279889237e-30f, 1.130996289e-31f, 3.769987629e-33f, 1.216125042e-34f, 3.800390755e-36f, 1.151633562e-37f}
+#define PST_FACT_TABLE {1.000000000e+00f, 1.000000000e+00f, 2.000000000e+00f, 6.000000000e+00f,                   \
+    2.400000000e+01f, 1.200000000e+02f, 7.200000000e+02f, 5.040000000e+03f, 4.032000000e+04f, 3.628800000e+05f,   \
+    3.628800000e+06f, 3.991680000e+07f, 4.790016000e+08f, 6.227020800e+09f, 8.717829120e+10f, 1.307674368e+12f,   \
+    2.092278989e+13f, 3.556874281e+14f, 6.402373706e+15f, 1.216451004e+17f, 2.432902008e+18f, 5.109094217e+19f,   \
+    1.124000728e+21f, 2.585201674e+22f, 6.204484017e+23f, 1.551121004e+25f, 4.032914611e+26f, 1.088886945e+28f,   \
+    3.048883446e+29f, 8.841761994e+30f, 2.652528598e+32f, 8.222838654e+33f, 2.631308369e+35f, 8.683317619e+36f}
 
 #ifndef HY_MIN_CTAS
 #define HY_MIN_CTAS 7     // 28 warps/SM: 72 registers and 28.9 KB of queues per CTA
@@ -216,8 +224,9 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * (int64_t)((Q + 31u) / 32u);
   const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
   const uint32_t key0 = key.k0[0], key1 = key.k1[0];
-  constexpr float inv_fact[17] = PST_INV_FACT_TABLE;
-  static_assert(KFIX >= 2 && KFIX <= 16, "KFIX out of range");
+  constexpr float inv_fact[34] = PST_INV_FACT_TABLE;
+  constexpr float fact[34] = PST_FACT_TABLE;
+  static_assert(KFIX >= 2 && KFIX - 1 + HY_STAGE2 <= 33, "t_k = P(k) k! must stay in fp32 range through stage 2");
   int ns = 0, ng = 0;                         // queue fill, warp-uniform
   uint32_t flag = 0;
   const uint64_t keep = l2_policy_evict_last();
@@ -227,19 +236,21 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     const bool act = lane < cnt;
     const int e = first + lane;
     const float4 st = act ? wq.se[e] : make_float4(0.f, 1.f, 0.f, 0.f);
-    float pp = st.x * inv_fact[KFIX - 1], dd = st.y;       // back to P(KFIX-1)
+    float tt = st.x, dd = st.y;                            // t = P(KFIX-1) (KFIX-1)!
     const float aa = st.z, qq = st.w;
     int cn = KFIX;
-    // second stage: HY_STAGE2 further terms unrolled with compile-time k (4-5 instructions per
-    // term instead of 8 in the generic loop below), frozen-cdf guard every 4 terms
+    // second stage: HY_STAGE2 further terms in the head's form t_k = P(k) k! with compile-time k
+    // (4 instructions per term instead of 8 in the generic loop below); frozen-cdf guard every 4
+    // terms (P(k) <= 2e-8 means u is beyond what the fp32 cdf can reach: stop counting)
 #pragma unroll
     for (int s2 = 0; s2 < HY_STAGE2; ++s2) {
       const int k = KFIX - 1 + s2;
-      pp *= fmaf(qq, (float)k, aa) * (1.0f / (float)(k + 1));  // P(k+1)
-      dd += pp;
+      tt *= fmaf(qq, (float)k, aa);                          // t_{k+1}
+      dd = fmaf(tt, inv_fact[k + 1], dd);                    // cdf(k+1) - u
       cn += (int)(__float_as_uint(dd) >> 31);
-      if ((s2 & 3) == 3) dd = (pp > 2.0e-8f) ? dd : 1.0f;
+      if ((s2 & 3) == 3) dd = (tt > 2.0e-8f * fact[k + 1]) ? dd : 1.0f;
     }
+    float pp = tt * inv_fact[KFIX - 1 + HY_STAGE2];          // back to P(k) for the open-ended loop
     float kf = (float)(KFIX - 1 + HY_STAGE2);
     for (int it = 0; it < HY_KMAX / 4; ++it) {
       if (!__any_sync(0xffffffffu, dd < 0.f)) break;          // every cdf has passed its u
@@ -425,7 +436,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         t[j] = ex2_fast(e2[j]);                     // P(0)
-        d[j] = t[j] - u01(rw[j]);                   // cdf(0) - u
+        d[j] = t[j] - u01_closed_top(rw[j]);        // cdf(0) - u
         cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
       }
       }  // !ALL_MIX
@@ -761,7 +772,6 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
     switch (kfix) {
       case 6: PST_LAUNCH_HYBRID(6, false); break;
       case 8: PST_LAUNCH_HYBRID(8, false); break;
-      case 12: PST_LAUNCH_HYBRID(12, false); break;
       default: PST_LAUNCH_HYBRID(HY_KFIX, false); break;
     }
 #else

@@ -4,6 +4,5 @@
 run() { echo "== $*"; env "$@" python tools/sampler_bench.py --cells 200000 --samplers hybrid --reps 3 2>&1 | grep -E "^hybrid|rror"; }
 run PST_HY_KFIX=8
 run PST_HY_KFIX=10
-run PST_HY_KFIX=12
 run PST_HY_MU_MAX=24 PST_HY_VAR_MAX=300
 run PST_HY_MU_MAX=48 PST_HY_VAR_MAX=900
