@@ -5,4 +5,5 @@ run() { echo "== $*"; env "$@" python tools/sampler_bench.py --cells 200000 --sa
 run PST_HY_KFIX=8
 run PST_HY_KFIX=10
 run PST_HY_MU_MAX=24 PST_HY_VAR_MAX=300
-run PST_HY_MU_MAX=48 PST_HY_VAR_MAX=900
+run PST_HY_MU_MAX=40 PST_HY_VAR_MAX=600
+run PST_HY_KFIX=8 PST_HY_MU_MAX=24 PST_HY_VAR_MAX=300
