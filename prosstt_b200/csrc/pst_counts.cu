@@ -358,6 +358,11 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         bm[j] = ok ? beta_m1[g0 + j] : 1.f;
       }
     }
+    // theta = alpha*mu + (beta-1) >= beta-1 when alpha, mu >= 0, so the Poisson-limit series below can
+    // only be needed in chunks where some gene has beta-1 < 0.1 (or a negative alpha): one vote per chunk
+    const bool chunk_small_theta = __any_sync(
+        0xffffffffu, fminf(fminf(bm[0], bm[1]), fminf(bm[2], bm[3])) < 0.1f ||
+                         fminf(fminf(al[0], al[1]), fminf(al[2], al[3])) < 0.f);
     // Per-cell metadata (cell id, tree row, library size) is the same for every lane: lane l
     // loads it for cell (group*32 + l) with one coalesced request per 32 cells and the loop
     // broadcasts it with shuffles.  The means quad of the next cell is prefetched: register load
@@ -423,7 +428,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * t1 <= var_max);
       }
       // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
-      if (fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < 0.1f) {
+      if (chunk_small_theta && fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < 0.1f) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float x = th[j];
@@ -472,10 +477,10 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         to_search[j] = (VEC || g0 + j < G) && small[j] && (d[j] < 0.f);
-        out[j] = small[j] ? cnt[j] : 0;
+        out[j] = cnt[j];
       }
-      // store the quad: undecided slots hold KFIX and mixture slots 0 until their queue entry is
-      // drained (the __syncwarp below orders this store before the drain's)
+      // store the quad: undecided and mixture slots hold a partial count until their queue entry is
+      // drained, which always writes them (the __syncwarp below orders this store before the drain's)
       {
         int32_t *dst = X + ((uint64_t)(uint32_t)cell * ldx + g0);
         if (VEC) {
