@@ -1047,3 +1047,25 @@ def test_narrow_host_output_is_lossless(tdt):
         sim.sample_density(t, n, shard=(rank, 2), host_out=(h, rest[0][lo:hi], rest[1][lo:hi], rest[2][lo:hi], o), **kw)
         parts.append(formats.widen(h.numpy(), o))
     assert np.array_equal(np.concatenate(parts), X32)
+
+
+def test_large_cell_count_draw_is_partition_consistent():
+    """More than 2^24 cells in one launch (few genes): a piece drawn separately with the matching
+    cell offset equals the same rows of the big draw, and the totals match the model."""
+    dev = torch.device(DEV)
+    t = ptree.Tree(topology=[[0, 1], [0, 2]], time={0: 4, 1: 4, 2: 4}, num_branches=3, branch_points=1, modules=3, G=8)
+    rng = np.random.RandomState(2)
+    t.add_genes({b: np.exp(rng.normal(1.0, 1.5, (4, 8))) for b in t.branches})
+    tb = TreeTables(t, dev)
+    eng = CountEngine(t, tb, np.full(8, 0.3), np.full(8, 2.0), dev, sampler="hybrid")
+    n = (1 << 24) + 5000
+    g = torch.Generator(device=dev).manual_seed(3)
+    rows = torch.randint(0, 12, (n,), device=dev, dtype=torch.int32, generator=g)
+    s32 = torch.exp(torch.randn(n, device=dev, generator=g) * 0.7)
+    X = eng.draw(rows, s32, 77, 1000)
+    eng.check()
+    lo = (1 << 24) - 3000
+    part = eng.draw(rows[lo:], s32[lo:], 77, 1000 + lo)
+    assert torch.equal(X[lo:], part)
+    mu = torch.from_numpy(np.concatenate([t.means[b] for b in t.branches])).to(dev)[rows.long()].float() * s32[:, None]
+    assert abs(float(X.double().mean() / mu.double().mean()) - 1.0) < 2e-3
