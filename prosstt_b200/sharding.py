@@ -4,7 +4,9 @@ The path has no data-path collective: every rank holds the small replicated stat
 its own contiguous slice of the cells with `shard=(rank, world)`; all random streams are keyed by
 the global cell index, so the union of the slices is bit-identical to the single-GPU result.
 `gather_counts` is the optional epilogue: an all_gather of the slabs (NCCL over NVLink/NVSwitch
-when the tensors live on GPUs, gloo on CPU tensors)."""
+when the tensors live on GPUs, gloo on CPU tensors).  `allreduce_gene_stats` is the cheap one: the
+per-gene sums of `stats.count_stats` (a few hundred KB) summed over the ranks, so every rank holds the
+whole-job gene mean / variance / zero fraction without moving a count."""
 import os
 
 import torch
@@ -38,3 +40,13 @@ def gather_counts(local, n_total, group=None):
     slabs = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(slabs, mine.contiguous(), group=group)
     return torch.cat([s[:hi - lo] for s, (lo, hi) in zip(slabs, sizes)])
+
+
+def allreduce_gene_stats(stats, n_local, group=None):
+    """Sum the per-gene fields of a `stats.count_stats` result (gene_sum, gene_sumsq, gene_zeros)
+    and the number of cells over all ranks, in place.  Returns (stats, n_total).  The per-cell
+    fields stay rank-local (they belong to this rank's cells)."""
+    n = torch.tensor([int(n_local)], dtype=torch.int64, device=stats["gene_sum"].device)
+    for t in (stats["gene_sum"], stats["gene_sumsq"], stats["gene_zeros"], n):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return stats, int(n.item())

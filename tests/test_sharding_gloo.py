@@ -42,6 +42,14 @@ def _worker(rank, world, port, n_cells, seed, out_dir):
     from prosstt_b200.sharding import gather_counts, rank_and_world, shard_range
     assert rank_and_world() == (rank, world) and shard_range(n_cells, rank, world) == (lo, hi)
     full = gather_counts(local.reshape(-1, 1), n_cells).reshape(-1)      # the optional gather epilogue
+    # the cheap epilogue: per-gene summaries summed over ranks (fields as stats.count_stats returns them)
+    from prosstt_b200.sharding import allreduce_gene_stats
+    Xl = (local.reshape(-1, 1) * torch.arange(1, 4)).to(torch.int64)      # (n_local, 3) pseudo counts
+    st = {"gene_sum": Xl.sum(0), "gene_sumsq": (Xl * Xl).sum(0), "gene_zeros": (Xl == 0).sum(0)}
+    st, n_tot = allreduce_gene_stats(st, hi - lo)
+    Xf = (full.reshape(-1, 1) * torch.arange(1, 4)).to(torch.int64)
+    assert n_tot == n_cells and torch.equal(st["gene_sum"], Xf.sum(0))
+    assert torch.equal(st["gene_sumsq"], (Xf * Xf).sum(0)) and torch.equal(st["gene_zeros"], (Xf == 0).sum(0))
     tmax = torch.tensor([float(rank + 1)])
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)          # the bench's max-over-ranks timing
     if rank == 0:

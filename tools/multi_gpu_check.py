@@ -14,7 +14,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from prosstt_b200 import simulation as sim  # noqa: E402
-from prosstt_b200.sharding import gather_counts  # noqa: E402
+from prosstt_b200.sharding import allreduce_gene_stats, gather_counts  # noqa: E402
+from prosstt_b200.stats import count_stats  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -34,12 +35,18 @@ for name, call in (
     total = torch.tensor([X.shape[0]], device=dev)
     dist.all_reduce(total)
     gathered = gather_counts(X, int(total.item()))               # NCCL over NVLink
+    # the cheap epilogue: per-gene summaries of the local slab, summed over the ranks (NCCL all_reduce)
+    st, n_tot = allreduce_gene_stats(count_stats(X), X.shape[0])
     if rank == 0:
         whole = call()[0]
         same = torch.equal(gathered, whole)
-        ok &= same
-        print("%-26s world=%d cells=%d genes=%d  gathered shards == single-GPU result: %s  (sum %d)"
-              % (name, world, whole.shape[0], whole.shape[1], same, int(whole.sum(dtype=torch.int64))), flush=True)
+        ws = count_stats(whole)
+        stats_same = n_tot == whole.shape[0] and all(torch.equal(st[k], ws[k]) for k in ("gene_sum", "gene_sumsq", "gene_zeros"))
+        ok &= same and stats_same
+        print("%-26s world=%d cells=%d genes=%d  gathered shards == single-GPU result: %s  all-reduced gene stats == "
+              "single-GPU stats: %s  (sum %d)"
+              % (name, world, whole.shape[0], whole.shape[1], same, stats_same, int(whole.sum(dtype=torch.int64))),
+              flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
