@@ -8,8 +8,9 @@
 //   X     ~ NB(r, 1/(1+theta))  ==  Poisson( theta * Gamma(r) )
 //
 // Work item = (cell, gene quad): one thread draws 4 neighbouring genes of one cell and
-// writes them with one 128-bit store; a warp writes 512 contiguous bytes of X.  Items are a
-// flat range so the grid is load-balanced for any G.  Every uniform is a pure function of
+// writes them with one 128-bit store; a warp writes 512 contiguous bytes of X.  Work is cut
+// into chunks (32 quads x 64 cells) that persistent warps claim from an atomic counter, so the
+// grid is load-balanced for any G and any mix of means.  Every uniform is a pure function of
 // (seed, cell, gene or gene quad, draw index) through Philox4x32-10, so counts do not depend
 // on launch shape, cell partition or GPU count.
 //
@@ -158,8 +159,8 @@ __device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
 // Large means are pushed to a second per-warp queue and drawn 32 at a time by the mixture
 //   (Marsaglia-Tsang + PTRS) on their own per-(cell, gene) Philox stream; the draw is a
 //   restartable step (mixture_step): rejected entries are re-queued, no warp spins in a loop.
-// The head writes the quad with one 128-bit store (0 in undecided slots); queue results are
-//   written with 4-byte stores after a __syncwarp (same warp, ordered).
+// The head writes the quad with one 128-bit store (a partial count in undecided and mixture
+//   slots); queue results overwrite them with 4-byte stores after a __syncwarp (same warp, ordered).
 // The route depends on the parameters only, never on the uniforms, so the draw is unbiased.
 // Work decomposition, prefetching and the dynamic chunk scheduler are described at the loop.
 // ---------------------------------------------------------------------------
@@ -178,7 +179,7 @@ constexpr int HY_KFIX = 10;                                  // unrolled head te
 static_assert(HY_MU_MAX <= 32.0f && HY_KFIX >= 10, "frozen-cdf guard needs P(k>=KFIX-1) > 2e-8 before the mode");
 
 struct HyWarpQueues {
-  float4 se[HY_QCAP];       // inversion tail: P(k), cdf(k)-u, a, q
+  float4 se[HY_QCAP];       // inversion tail: t = P(k) k! at k = KFIX-1, cdf(k)-u, a, q
   int2 sw[HY_QCAP];         //                 where the count goes: (cell, gene)
   float4 ge[HY_QCAP];       // mixture: mu (or lambda once the gamma is accepted), theta, cell, gene
   int ga[HY_QCAP];          //          attempt counter of the current stage | stage << 16
