@@ -138,6 +138,33 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   return MixResult{k, MIX_DONE};
 }
 
+// Rare path of the inversion (about 1e-6 of the inverted counts).  The fp32 pmf carries a relative
+// error of ~1e-6 (MUFU lg2 / ex2 / rcp in P(0)), so the computed cdf can top out at 1 - 1e-6; a uniform
+// above that never finds its crossing and the search freezes far out in the tail (the 1 - 3e-8
+// quantile), which shows as a spike there in histograms of 1e9 draws.  Such a count is redrawn
+// from the same distribution with a fresh uniform (block 0xffffffff of the count's own Philox stream,
+// which the mixture never reaches), so the lost mass is spread over the distribution in proportion.
+//   a = q r, q = theta/(1+theta):  P(0) = (1-q)^r,  log2 P(0) = a log2(1-q)/q
+__device__ __noinline__ int redraw_inversion(float a, float q, uint32_t key0, uint32_t key1, uint32_t gene,
+                                             int64_t cell, int kmax) {
+  const uint32_t c1 = (uint32_t)cell, c2 = (TAG_COUNT << 16) | (uint32_t)((uint64_t)cell >> 32);
+  const uint4 w = philox_s(key0, key1, gene, c1, c2, 0xffffffffu);
+  const float u = u01(w.x);
+  const float l = (q < 0.05f)       // log2(1-q)/q, by series towards the Poisson limit q -> 0
+      ? -1.4426950409f * fmaf(q, fmaf(q, fmaf(q, fmaf(q, 0.2f, 0.25f), 0.3333333333f), 0.5f), 1.0f)
+      : log2f(1.0f - q) / q;
+  const float mu = a / (1.0f - q);
+  float p = exp2f(a * l), cdf = p;
+  int k = 0;
+  while (cdf < u && k < kmax) {
+    p *= fmaf(q, (float)k, a) / (float)(k + 1);
+    cdf += p;
+    ++k;
+    if (p <= 2.0e-8f && (float)k > mu) break;      // frozen again (probability ~1e-12): keep k
+  }
+  return k;
+}
+
 __device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
   return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
 }
@@ -168,6 +195,7 @@ constexpr int HY_WARPS = 4;                  // warps per CTA
 constexpr int HY_THREADS = HY_WARPS * 32;
 constexpr int HY_QCAP = 160;                 // 31 carried + 128 new entries, rounded up
 constexpr int HY_KMAX = 2048;                // hard bound on inversion terms
+constexpr float HY_FROZEN = 2.0f;            // cdf(k)-u sentinel (natural values are <= 1): the search froze below u
 #ifndef HY_STAGE2
 #define HY_STAGE2 24                         // unrolled terms at the start of the tail
 #endif
@@ -186,19 +214,13 @@ struct HyWarpQueues {
   float4 mstage[32];        // next cell's means quad, filled by cp.async (one slot per lane)
 };
 
-// 1/k! and k!, k = 0..33 (immediates after unrolling; 1/33! = 1.15e-37 is the last normal fp32 value of the series)
+// 1/k!, k = 0..33 (immediates after unrolling; 1/33! = 1.15e-37 is the last normal fp32 value of the series)
 #define PST_INV_FACT_TABLE {1.000000000e+00f, 1.000000000e+00f, 5.000000000e-01f, 1.666666667e-01f,               \
     4.166666667e-02f, 8.333333333e-03f, 1.388888889e-03f, 1.984126984e-04f, 2.480158730e-05f, 2.755731922e-06f,   \
     2.755731922e-07f, 2.505210839e-08f, 2.087675699e-09f, 1.605904384e-10f, 1.147074560e-11f, 7.647163732e-13f,   \
     4.779477332e-14f, 2.811457254e-15f, 1.561920697e-16f, 8.220635247e-18f, 4.110317623e-19f, 1.957294106e-20f,   \
     8.896791392e-22f, 3.868170171e-23f, 1.611737571e-24f, 6.446950284e-26f, 2.479596263e-27f, 9.183689864e-29f,   \
     3.279889237e-30f, 1.130996289e-31f, 3.769987629e-33f, 1.216125042e-34f, 3.800390755e-36f, 1.151633562e-37f}
-#define PST_FACT_TABLE {1.000000000e+00f, 1.000000000e+00f, 2.000000000e+00f, 6.000000000e+00f,                   \
-    2.400000000e+01f, 1.200000000e+02f, 7.200000000e+02f, 5.040000000e+03f, 4.032000000e+04f, 3.628800000e+05f,   \
-    3.628800000e+06f, 3.991680000e+07f, 4.790016000e+08f, 6.227020800e+09f, 8.717829120e+10f, 1.307674368e+12f,   \
-    2.092278989e+13f, 3.556874281e+14f, 6.402373706e+15f, 1.216451004e+17f, 2.432902008e+18f, 5.109094217e+19f,   \
-    1.124000728e+21f, 2.585201674e+22f, 6.204484017e+23f, 1.551121004e+25f, 4.032914611e+26f, 1.088886945e+28f,   \
-    3.048883446e+29f, 8.841761994e+30f, 2.652528598e+32f, 8.222838654e+33f, 2.631308369e+35f, 8.683317619e+36f}
 
 #ifndef HY_MIN_CTAS
 #define HY_MIN_CTAS 7     // 28 warps/SM: 72 registers and 28.9 KB of queues per CTA
@@ -226,7 +248,6 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
   const uint32_t key0 = key.k0[0], key1 = key.k1[0];
   constexpr float inv_fact[34] = PST_INV_FACT_TABLE;
-  constexpr float fact[34] = PST_FACT_TABLE;
   static_assert(KFIX >= 2 && KFIX - 1 + HY_STAGE2 <= 33, "t_k = P(k) k! must stay in fp32 range through stage 2");
   int ns = 0, ng = 0;                         // queue fill, warp-uniform
   uint32_t flag = 0;
@@ -241,15 +262,13 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     const float aa = st.z, qq = st.w;
     int cn = KFIX;
     // second stage: HY_STAGE2 further terms in the head's form t_k = P(k) k! with compile-time k
-    // (4 instructions per term instead of 8 in the generic loop below); frozen-cdf guard every 4
-    // terms (P(k) <= 2e-8 means u is beyond what the fp32 cdf can reach: stop counting)
+    // (4 instructions per term instead of 8 in the generic loop below)
 #pragma unroll
     for (int s2 = 0; s2 < HY_STAGE2; ++s2) {
       const int k = KFIX - 1 + s2;
       tt *= fmaf(qq, (float)k, aa);                          // t_{k+1}
       dd = fmaf(tt, inv_fact[k + 1], dd);                    // cdf(k+1) - u
       cn += (int)(__float_as_uint(dd) >> 31);
-      if ((s2 & 3) == 3) dd = (tt > 2.0e-8f * fact[k + 1]) ? dd : 1.0f;
     }
     float pp = tt * inv_fact[KFIX - 1 + HY_STAGE2];          // back to P(k) for the open-ended loop
     float kf = (float)(KFIX - 1 + HY_STAGE2);
@@ -263,13 +282,14 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         cn += (int)(__float_as_uint(dd) >> 31);
         kf = k1;
       }
-      // u beyond what the fp32 cdf can reach (probability ~1e-7): stop counting
-      dd = (pp > 2.0e-8f) ? dd : 1.0f;
+      // u beyond what the fp32 cdf can reach: stop counting, mark the entry for the redraw
+      dd = (pp <= 2.0e-8f && dd < 0.f) ? HY_FROZEN : dd;
     }
-    if (act) {
-      const int2 w = wq.sw[e];
-      X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
+    const int2 w = act ? wq.sw[e] : make_int2(0, 0);
+    if (__any_sync(0xffffffffu, dd == HY_FROZEN)) {          // about one batch in 10^4
+      if (dd == HY_FROZEN) cn = redraw_inversion(aa, qq, key0, key1, (uint32_t)w.y, cell0 + w.x, HY_KMAX);
     }
+    if (act) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
   };
   // one mixture step for up to 32 queued entries; rejected entries go back to the queue (returns
   // how many), so the warp never spins in a rejection loop
