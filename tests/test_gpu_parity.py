@@ -1069,3 +1069,25 @@ def test_large_cell_count_draw_is_partition_consistent():
     assert torch.equal(X[lo:], part)
     mu = torch.from_numpy(np.concatenate([t.means[b] for b in t.branches])).to(dev)[rows.long()].float() * s32[:, None]
     assert abs(float(X.double().mean() / mu.double().mean()) - 1.0) < 2e-3
+
+
+def test_inversion_has_no_spike_where_the_search_freezes():
+    """The fp32 pmf of the inversion is scaled by 1 - eps (eps ~ 1e-6), so uniforms above the top of the
+    computed cdf never cross it.  They used to end where the search froze (mu = 14: k = 90, 1.3e-6 of the
+    draws against an exact tail of 3e-8); they are redrawn now.  2e8 draws: the exact expectation beyond
+    k = 85 is 21 counts, the spike would be ~260."""
+    import scipy.stats
+    mu, alpha, beta = 14.0, 0.1, 2.5
+    t = _flat_tree(np.full(4, mu))
+    dev = torch.device(DEV)
+    eng = CountEngine(t, TreeTables(t, dev), np.full(4, alpha), np.full(4, beta), dev, sampler="hybrid")
+    n = 50_000_000
+    X = eng.draw(torch.zeros(n, dtype=torch.int32, device=dev), torch.ones(n, dtype=torch.float32, device=dev), 31337, 0)
+    eng.check()
+    theta = alpha * mu + beta - 1
+    expect = scipy.stats.nbinom.sf(85, mu / theta, 1 / (1 + theta)) * 4 * n
+    far = int((X > 85).sum().item())
+    assert 15 < expect < 30 and far <= expect + 6 * np.sqrt(expect), (far, expect)
+    assert int(X.max().item()) < 110
+    # the body is untouched: mean within 5 sigma
+    assert abs(X.double().mean().item() - mu) < 5 * np.sqrt((alpha * mu * mu + beta * mu) / (4 * n))
