@@ -75,10 +75,15 @@ __device__ __forceinline__ uint4 philox_s(uint32_t k0, uint32_t k1, uint32_t c0,
 __device__ __forceinline__ float u01(uint32_t w) {
   return fminf(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
 }
-// the same without the clamp: (0,1], and 1.0 only for the top 128 values of w (3e-8).  For the
-// cdf inversion, whose search stops where the fp32 cdf freezes, u = 1 is just the extreme quantile
-__device__ __forceinline__ float u01_closed_top(uint32_t w) {
-  return fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+// The uniform of the NB cdf inversion, stretched to (0, 1 + 8e-6].  The fp32 pmf of the inversion
+// is exact up to a common factor 1 + eps, |eps| <= ~4e-6 (MUFU lg2/ex2/rcp in P(0)), so its cdf tops
+// out anywhere in 1 +- 4e-6.  Stretching u by more than that makes the error one-sided: a u above the
+// top of the computed cdf (probability ~8e-6) is detected when the search freezes and the count is
+// redrawn, so the accepted draws follow pmf/(1+eps) renormalised, i.e. the exact pmf, and no part of
+// the upper tail is cut off.  Same cost as the plain conversion: one I2FP and one FFMA.
+constexpr float kInversionStretch = 8.0e-6f;
+__device__ __forceinline__ float u01_inversion(uint32_t w) {
+  return fmaf((float)w, 2.3283064365386963e-10f * (1.0f + kInversionStretch), 1.1641532182693481e-10f);
 }
 // 53-bit double in [0,1) exactly as numpy's legacy random_sample builds it
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {

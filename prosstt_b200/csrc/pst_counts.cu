@@ -138,12 +138,14 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   return MixResult{k, MIX_DONE};
 }
 
-// Rare path of the inversion (about 1e-6 of the inverted counts).  The fp32 pmf carries a relative
-// error of ~1e-6 (MUFU lg2 / ex2 / rcp in P(0)), so the computed cdf can top out at 1 - 1e-6; a uniform
-// above that never finds its crossing and the search freezes far out in the tail (the 1 - 3e-8
-// quantile), which shows as a spike there in histograms of 1e9 draws.  Such a count is redrawn
-// from the same distribution with a fresh uniform (block 0xffffffff of the count's own Philox stream,
-// which the mixture never reaches), so the lost mass is spread over the distribution in proportion.
+// Rare path of the inversion (about 1e-5 of the inverted counts).  The fp32 pmf is exact up to a
+// common factor 1 + eps (|eps| up to ~4e-6, from the MUFU lg2 / ex2 / rcp in P(0)); the uniform is
+// stretched to (0, 1 + 8e-6] (u01_inversion) so that the computed cdf always tops out below the
+// largest u.  A uniform above the top never finds its crossing: the search freezes far out in the
+// tail and the count is redrawn here from the same distribution with a fresh uniform (block
+// 0xffffffff of the count's own Philox stream, which the mixture never reaches).  Accepted and
+// redrawn counts together follow the exact pmf; without this the lost mass would pile up at the
+// 1 - 3e-8 quantile (undershoot) or the top eps quantile would never be produced (overshoot).
 //   a = q r, q = theta/(1+theta):  P(0) = (1-q)^r,  log2 P(0) = a log2(1-q)/q
 __device__ __noinline__ int redraw_inversion(float a, float q, uint32_t key0, uint32_t key1, uint32_t gene,
                                              int64_t cell, int kmax) {
@@ -286,7 +288,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       dd = (pp <= 2.0e-8f && dd < 0.f) ? HY_FROZEN : dd;
     }
     const int2 w = act ? wq.sw[e] : make_int2(0, 0);
-    if (__any_sync(0xffffffffu, dd == HY_FROZEN)) {          // about one batch in 10^4
+    if (__any_sync(0xffffffffu, dd == HY_FROZEN)) {          // about one batch in 10^3
       if (dd == HY_FROZEN) cn = redraw_inversion(aa, qq, key0, key1, (uint32_t)w.y, cell0 + w.x, HY_KMAX);
     }
     if (act) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
@@ -462,7 +464,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         t[j] = ex2_fast(e2[j]);                     // P(0)
-        d[j] = t[j] - u01_closed_top(rw[j]);        // cdf(0) - u
+        d[j] = t[j] - u01_inversion(rw[j]);         // cdf(0) - u
         cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
       }
       }  // !ALL_MIX
