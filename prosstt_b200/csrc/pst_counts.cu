@@ -208,6 +208,17 @@ constexpr int HY_KFIX = 10;                                  // unrolled head te
 // smallest such value is Poisson(32) at k = 9: 1.2e-6.  Larger HY_MU_MAX would break that.
 static_assert(HY_MU_MAX <= 32.0f && HY_KFIX >= 10, "frozen-cdf guard needs P(k>=KFIX-1) > 2e-8 before the mode");
 
+// 1/(k+1) for the open-ended part of the search drain, k = K_TAIL0 + j: read four at a time from the
+// constant bank with a warp-uniform index instead of one MUFU.RCP per term
+constexpr int HY_TAIL0 = HY_KFIX - 1 + HY_STAGE2;          // first k of the open-ended loop (33)
+struct RcpTail { float v[HY_KMAX]; };
+__host__ __device__ constexpr RcpTail make_rcp_tail() {
+  RcpTail t{};
+  for (int j = 0; j < HY_KMAX; ++j) t.v[j] = 1.0f / (float)(HY_TAIL0 + j + 1);
+  return t;
+}
+__constant__ __align__(16) RcpTail c_rcp_tail = make_rcp_tail();
+
 struct HyWarpQueues {
   float4 se[HY_QCAP];       // inversion tail: t = P(k) k! at k = KFIX-1, cdf(k)-u, a, q
   int2 sw[HY_QCAP];         //                 where the count goes: (cell, gene)
@@ -273,16 +284,23 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       cn += (int)(__float_as_uint(dd) >> 31);
     }
     float pp = tt * inv_fact[KFIX - 1 + HY_STAGE2];          // back to P(k) for the open-ended loop
-    float kf = (float)(KFIX - 1 + HY_STAGE2);
+    float ak = fmaf(qq, (float)(KFIX - 1 + HY_STAGE2), aa);  // a + q k, advanced by one FADD per term
     for (int it = 0; it < HY_KMAX / 4; ++it) {
       if (!__any_sync(0xffffffffu, dd < 0.f)) break;          // every cdf has passed its u
+      float rk[4];
+      if constexpr (KFIX == HY_KFIX) {                        // 1/(k+1) for the next four k: one constant load
+        const float4 r4 = reinterpret_cast<const float4 *>(c_rcp_tail.v)[it];
+        rk[0] = r4.x; rk[1] = r4.y; rk[2] = r4.z; rk[3] = r4.w;
+      } else {                                                // developer builds with another head length
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) rk[s4] = rcp_fast((float)(KFIX + HY_STAGE2 + 4 * it + s4));
+      }
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
-        const float k1 = kf + 1.0f;
-        pp *= fmaf(qq, kf, aa) * rcp_fast(k1);                 // P(k+1)
+        pp *= ak * rk[s4];                                     // P(k+1) = P(k) (a + q k)/(k+1)
         dd += pp;                                              // cdf(k+1) - u
         cn += (int)(__float_as_uint(dd) >> 31);
-        kf = k1;
+        ak += qq;
       }
       // u beyond what the fp32 cdf can reach: stop counting, mark the entry for the redraw
       dd = (pp <= 2.0e-8f && dd < 0.f) ? HY_FROZEN : dd;
