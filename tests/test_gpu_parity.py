@@ -1091,3 +1091,34 @@ def test_inversion_has_no_spike_where_the_search_freezes():
     assert int(X.max().item()) < 110
     # the body is untouched: mean within 5 sigma
     assert abs(X.double().mean().item() - mu) < 5 * np.sqrt((alpha * mu * mu + beta * mu) / (4 * n))
+
+
+def test_empty_and_ragged_partitions():
+    """No cells at all, and more ranks than cells: every sampler and epilogue accepts empty slices and
+    the union of the slices is still the whole."""
+    from prosstt_b200 import formats, stats as pstats
+    t, alpha, beta = _bench_like_tree(1, 6, 3, 12, seed=4)
+    X, pt, br, sc = sim.sample_density(t, 0, alpha, beta, seed=3, device=DEV)
+    assert X.shape == (0, 12) and len(pt) == len(br) == len(sc) == 0
+    whole = sim.sample_density(t, 3, alpha, beta, seed=3, device=DEV, dtype=np.int32)
+    parts = [sim.sample_density(t, 3, alpha, beta, seed=3, device=DEV, dtype=np.int32, shard=(r, 8)) for r in range(8)]
+    assert sorted(p[0].shape[0] for p in parts) == [0, 0, 0, 0, 0, 1, 1, 1]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), whole[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), whole[1])
+    assert list(np.concatenate([p[2] for p in parts])) == list(whole[2])
+    # host-streamed output of an empty slice
+    h = (torch.empty((0, 12), dtype=torch.int32), torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int32),
+         torch.empty(0, dtype=torch.float64))
+    Xh = sim.sample_density(t, 3, alpha, beta, seed=3, device=DEV, shard=(0, 8), host_out=h)[0]
+    assert Xh.shape == (0, 12)
+    # epilogues on an empty matrix
+    E = torch.empty((0, 12), dtype=torch.int32, device=DEV)
+    st = pstats.count_stats(E)
+    assert st["cell_total"].numel() == 0 and int(st["gene_sum"].sum()) == 0
+    assert pstats.log1p(E).shape == (0, 12)
+    indptr, indices, data = formats.to_csr(E)
+    assert indptr.tolist() == [0] and indices.numel() == 0 and data.numel() == 0
+    # whole-tree sampling with more ranks than positions per rank boundary
+    wt = sim.sample_whole_tree(t, 1, alpha, beta, seed=5, device=DEV, dtype=np.int32)
+    wparts = [sim.sample_whole_tree(t, 1, alpha, beta, seed=5, device=DEV, dtype=np.int32, shard=(r, 5)) for r in range(5)]
+    assert np.array_equal(np.concatenate([p[0] for p in wparts]), wt[0])
