@@ -37,7 +37,6 @@ struct PhiloxKey {
   uint32_t k0[10], k1[10];
   __host__ __device__ explicit PhiloxKey(uint64_t seed) {
     uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
-#pragma unroll
     for (int i = 0; i < 10; ++i) { k0[i] = a; k1[i] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
   }
 };
