@@ -6,5 +6,5 @@ for tool in memcheck racecheck; do
 done
 echo "== memcheck: lineage + index-map tests"
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -q -x -k "walks or index_maps or pick_branch or pearson or nb_params or domain" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Invalid" | head
-echo "== memcheck: epilogue kernels (stats, transforms, CSR, uint16 narrowing, base expression)"
-compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -q -x -k "count_stats or transform_counts or csr_compaction or narrow_u16 or base_gene_exp" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Invalid" | head
+echo "== memcheck: epilogue kernels (stats, transforms, CSR, narrow formats, base expression)"
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -q -x -k "count_stats or transform_counts or csr_compaction or narrow_kernel or base_gene_exp" 2>&1 | grep -E "ERROR SUMMARY|passed|failed|Invalid" | head
