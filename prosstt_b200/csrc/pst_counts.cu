@@ -236,7 +236,7 @@ struct HyWarpQueues {
     3.279889237e-30f, 1.130996289e-31f, 3.769987629e-33f, 1.216125042e-34f, 3.800390755e-36f, 1.151633562e-37f}
 
 #ifndef HY_MIN_CTAS
-#define HY_MIN_CTAS 7     // 28 warps/SM: 72 registers and 28.9 KB of queues per CTA
+#define HY_MIN_CTAS 7     // 28 warps/SM: up to 72 registers (69 used) and 29.5 KB of queues per CTA
 #endif
 constexpr int HY_CHUNK_CELLS = 64;           // cells per chunk (x 32 quads = 8192 counts)
 
