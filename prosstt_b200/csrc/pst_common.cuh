@@ -79,10 +79,12 @@ __device__ __forceinline__ float u01(uint32_t w) {
 // out anywhere in 1 +- 4e-6.  Stretching u by more than that makes the error one-sided: a u above the
 // top of the computed cdf (probability ~8e-6) is detected when the search freezes and the count is
 // redrawn, so the accepted draws follow pmf/(1+eps) renormalised, i.e. the exact pmf, and no part of
-// the upper tail is cut off.  Same cost as the plain conversion: one I2FP and one FFMA.
+// the upper tail is cut off.
 constexpr float kInversionStretch = 8.0e-6f;
-__device__ __forceinline__ float u01_inversion(uint32_t w) {
-  return fmaf((float)w, 2.3283064365386963e-10f * (1.0f + kInversionStretch), 1.1641532182693481e-10f);
+// cdf(0) - u with u = w 2^-32 (1 + stretch) in [0, 1 + 8e-6): no half-step offset (u = 0 is harmless for
+// an inversion, X = 0), so the conversion and the subtraction are one I2FP and one FFMA
+__device__ __forceinline__ float cdf0_minus_u(float p0, uint32_t w) {
+  return fmaf((float)w, -2.3283064365386963e-10f * (1.0f + kInversionStretch), p0);
 }
 // 53-bit double in [0,1) exactly as numpy's legacy random_sample builds it
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {

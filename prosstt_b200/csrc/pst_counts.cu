@@ -482,7 +482,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         t[j] = ex2_fast(e2[j]);                     // P(0)
-        d[j] = t[j] - u01_inversion(rw[j]);         // cdf(0) - u
+        d[j] = cdf0_minus_u(t[j], rw[j]);           // cdf(0) - u, one FFMA
         cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
       }
       }  // !ALL_MIX
@@ -507,7 +507,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       for (int k = 0; k < KFIX - 1; ++k) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          t[j] *= fmaf(q[j], (float)k, a[j]);                    // t_{k+1} = P(k+1) (k+1)!
+          t[j] *= (k == 0) ? a[j] : fmaf(q[j], (float)k, a[j]);  // t_{k+1} = P(k+1) (k+1)!
           d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
           cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
         }
