@@ -249,3 +249,17 @@ def test_widen_host_side():
         formats.widen(X16, (np.array([1]), np.array([70000])))          # a saturated element is not listed
     with pytest.raises(TypeError):
         formats.widen(X16.astype(np.int16), (np.array([], dtype=np.int64), np.array([], dtype=np.int32)))
+
+
+def test_epilogue_argument_checks_without_a_gpu():
+    """stats / formats reject anything that is not a 2-D int32 CUDA tensor before touching the library."""
+    import torch
+    from prosstt_b200 import formats, stats
+    cpu = torch.zeros((3, 4), dtype=torch.int32)
+    for fn in (stats.count_stats, stats.log1p, formats.to_csr):
+        with pytest.raises(TypeError):
+            fn(cpu)
+    with pytest.raises(TypeError):
+        stats.transform_counts(cpu.float(), None, "log1p")
+    with pytest.raises(TypeError):
+        formats.widen(np.zeros((2, 2), dtype=np.int32), (np.array([]), np.array([])))
