@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define PST_ABI_VERSION 1
+#define PST_ABI_VERSION 2
 
 /* bits of the device-side status word written by the sampling kernels */
 #define PST_FLAG_DOMAIN   1u  /* mu <= 0, non-finite, or alpha*mu+beta-1 <= 0: scipy's
@@ -42,6 +42,7 @@ extern "C" {
 #define PST_FLAG_ROW      2u  /* row_of_cell outside [0,P)                              */
 #define PST_FLAG_CLAMPED  4u  /* a count exceeded INT32_MAX and was clamped             */
 #define PST_FLAG_NOZONE   8u  /* pseudotime outside every timezone (pick_branch)        */
+#define PST_FLAG_SCRATCH  16u /* the scratch list of pst_draw_counts was too small      */
 
 /* which per-count algorithm pst_draw_counts runs */
 #define PST_SAMPLER_GAMMA_POISSON 0  /* Marsaglia-Tsang gamma, PTRS / inversion Poisson  */
@@ -162,6 +163,19 @@ int pst_base_gene_exp(uint64_t seed, uint32_t tag, const double *cap, int64_t G,
 int pst_nb_params(const double *alpha, const double *beta, const double *mu,
                   int64_t n_cells, int64_t G, double *out_p, double *out_r, void *stream);
 
+/* The SAME parameterisation in fp32, evaluated by the __device__ functions that pst_draw_counts
+ * inlines (MUFU rcp/lg2, the small-theta series): for element i with mean mu[i] and per-element
+ * alpha[i], beta_m1[i] = beta-1 it writes theta = alpha mu + beta - 1 (gamma scale; scipy's
+ * p = 1/(1+theta)), r = mu/theta (gamma shape, scipy's n), q = theta/(1+theta) = get_pr_umi's p,
+ * a = q r, log2 P(X=0) = -r log2(1+theta), and the route the hybrid sampler takes.  Parity hook
+ * on the arithmetic that actually runs (count_model.py:156-161). */
+#define PST_ROUTE_MIXTURE       0   /* gamma-Poisson mixture                                  */
+#define PST_ROUTE_INVERSION     1   /* inversion of the NB cdf (mean <= 32, sd <= 20, shape <= 48 or theta < 0.1) */
+#define PST_ROUTE_DOMAIN_ERROR  2   /* sets PST_FLAG_DOMAIN in the sampler                    */
+int pst_nb_params_f32(const float *mu, const float *alpha, const float *beta_m1, int64_t n,
+                      float *out_theta, float *out_r, float *out_q, float *out_a,
+                      float *out_log2p0, int32_t *out_route, void *stream);
+
 /* ---- the hot loop: draw_counts, simulation.py:602-651 ------------------------- */
 /* X[i][g] ~ NB(mean mu = means[row_of_cell[i]][g]*scaling[i],
  *              var  alpha[g]*mu^2 + beta[g]*mu)        i in [0,n), g in [0,G)
@@ -171,17 +185,23 @@ int pst_nb_params(const double *alpha, const double *beta, const double *mu,
  * cell0+i, draw index) - independent of how cells are split over calls/GPUs.
  * beta_m1[g] = beta[g]-1 formed in fp64 by the caller.  X row stride is ldx
  * elements (>= G).  flags: FOUR uint32 words, zeroed once by the caller: word 0 is OR-ed
- * with PST_FLAG_*; words 1-2 are the hybrid sampler's work-scheduler scratch (used and
- * reset to zero by every launch; launches sharing a status buffer must be stream-ordered);
- * word 3 is reserved.
+ * with PST_FLAG_*; words 1-3 are reserved (the work-scheduler words live in the library,
+ * one set per (device, stream), so concurrent launches on different streams are safe).
  * cell_order (optional, may be NULL): a permutation of [0,n) giving the order in which the
- * cells are visited (hybrid sampler only; see pst_group_cells_by_row). */
+ * cells are visited (hybrid sampler only; see pst_group_cells_by_row).
+ * scratch (hybrid sampler only; NULL otherwise): pst_draw_scratch_words(n, G) uint32 words,
+ * 16-byte aligned, private to this call until it has completed.  It receives the list of the
+ * counts whose uniform lies in the top 2^-14 (about 6e-5 n G entries of 16 bytes); a second
+ * small kernel inverts those in fp64 with a 64-bit uniform, which is what resolves the upper
+ * tail beyond the 1 - 1e-7 quantile.  Content on entry is ignored. */
+int64_t pst_draw_scratch_words(int64_t n, int64_t G);
 int pst_draw_counts(const float *means, int64_t P, int64_t G,
                     const int32_t *row_of_cell, const float *scaling,
                     const float *alpha, const float *beta_m1,
                     uint64_t seed, int64_t cell0, int64_t n,
                     int32_t *X, int64_t ldx, uint32_t *flags, int32_t sampler,
-                    const int32_t *cell_order, void *stream);
+                    const int32_t *cell_order, uint32_t *scratch, int64_t scratch_words,
+                    void *stream);
 
 /* Counting sort of the cells by tree row: order[] lists the cells of row 0, then row 1, ...
  * (arbitrary order inside a row).  bins: P uint32 words of scratch.  Feeding `order` to
@@ -200,7 +220,6 @@ int pst_count_stats(const int32_t *X, int64_t n, int64_t G, int64_t ldx, uint64_
                     uint32_t *cell_zeros, uint64_t *gene_sum, uint64_t *gene_sumsq,
                     uint64_t *gene_zeros, void *stream);
 
-#if defined(__GNUC__)
 /* ---- epilogues over the count matrix ------------------- */
 #define PST_TRANSFORM_NORMALIZE        0   /* X / scaling            (compare_axolotl.ipynb cell 14) */
 #define PST_TRANSFORM_NORMALIZE_LOG1P  1   /* log(X / scaling + 1)                                   */
@@ -228,6 +247,7 @@ int pst_narrow_counts(const int32_t *X, int64_t n, int64_t G, int64_t ldx, void 
                       int32_t out_bits, int64_t row0, int64_t *ovf_index, int32_t *ovf_value,
                       int64_t ovf_cap, uint64_t *ovf_count, void *stream);
 
+#if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PST_LIB", os.path.join(_PKG, "libprosstt_b200.so"))   # PST_LIB: developer override
 
 # flag bits (include/prosstt_b200.h)
-FLAG_DOMAIN, FLAG_ROW, FLAG_CLAMPED, FLAG_NOZONE = 1, 2, 4, 8
+FLAG_DOMAIN, FLAG_ROW, FLAG_CLAMPED, FLAG_NOZONE, FLAG_SCRATCH = 1, 2, 4, 8, 16
 SAMPLER_GAMMA_POISSON, SAMPLER_HYBRID = 0, 1
 SAMPLERS = {"gamma_poisson": SAMPLER_GAMMA_POISSON, "hybrid": SAMPLER_HYBRID}
 
@@ -43,7 +43,10 @@ _SIGNATURES = {
     "pst_scalings": (C.c_int, [_p, _i64, _p, _p, _p]),
     "pst_base_gene_exp": (C.c_int, [_u64, _u32, _p, _i64, _f64, _f64, _f64, _i32, _p, _p, _p, _p]),
     "pst_nb_params": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
-    "pst_draw_counts": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _u64, _i64, _i64, _p, _i64, _p, _i32, _p, _p]),
+    "pst_nb_params_f32": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "pst_draw_scratch_words": (_i64, [_i64, _i64]),
+    "pst_draw_counts": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _u64, _i64, _i64, _p, _i64, _p, _i32, _p, _p, _i64,
+                                  _p]),
     "pst_group_cells_by_row": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "pst_count_stats": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "pst_transform_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p]),
@@ -71,7 +74,7 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.pst_abi_version() != 1:
+    if lib.pst_abi_version() != 2:
         raise NativeError("prosstt_b200: ABI version mismatch")
     _lib = lib
     return lib
@@ -93,8 +96,16 @@ def device(dev=None):
     return torch.device(dev)
 
 
+class _StreamHandle(int):
+    """cudaStream_t as an integer that remembers its device: call() makes that device current
+    for the launch (the library launches on the CUDA runtime's current device)."""
+    dev = None
+
+
 def stream_ptr(dev):
-    return torch.cuda.current_stream(dev).cuda_stream
+    h = _StreamHandle(torch.cuda.current_stream(dev).cuda_stream)
+    h.dev = torch.device(dev)
+    return h
 
 
 def ptr(t):
@@ -108,9 +119,31 @@ def ptr(t):
 def call(name, *args):
     """Call a C-ABI entry point.  Tensor arguments are passed by device pointer and stay
     referenced until the launch has been issued (never take ptr() of a temporary: the
-    caching allocator would hand its block to the next allocation)."""
+    caching allocator would hand its block to the next allocation).
+
+    The library launches on the CUDA runtime's current device, so the call runs with the
+    device of its stream argument (stream_ptr(dev)) made current, and tensor arguments must
+    live on that device: a `device="cuda:1"` request works whatever device the caller's
+    thread has selected."""
     lib = load()
-    rc = getattr(lib, name)(*[ptr(a) if isinstance(a, torch.Tensor) else a for a in args])
+    raw, dev = [], None
+    for a in args:
+        if isinstance(a, _StreamHandle):
+            dev = a.dev
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise ValueError("%s: a tensor argument lives on %s but the call runs on %s" % (name, a.device, dev))
+            raw.append(ptr(a))
+        else:
+            raw.append(a)
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*raw)
+    else:
+        rc = getattr(lib, name)(*raw)
     if rc != 0:
         msg = lib.pst_last_error().decode("utf-8", "replace")
         if rc < 0:

@@ -19,7 +19,9 @@ int check_launch(const char *fn);   // cudaGetLastError -> status, counts the la
 
 #define PST_REQUIRE(cond, fn, what) do { if (!(cond)) return pst::fail_arg(fn, what); } while (0)
 
-constexpr int kNumSM = 148;          // B200: 2 dies x 74 SMs
+int num_sm();                        // SM count of the current device (148 on a B200), queried once per device
+#define PST_SCHED_SLOTS 4096
+int sched_slot(void *stream);        // scheduler scratch slot of (current device, stream) for pst_draw_counts
 
 // stream tags (third Philox counter word): one independent stream per use
 enum : uint32_t {
@@ -74,17 +76,22 @@ __device__ __forceinline__ uint4 philox_s(uint32_t k0, uint32_t k1, uint32_t c0,
 __device__ __forceinline__ float u01(uint32_t w) {
   return fminf(fmaf((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
 }
-// The uniform of the NB cdf inversion, stretched to (0, 1 + 8e-6].  The fp32 pmf of the inversion
-// is exact up to a common factor 1 + eps, |eps| <= ~4e-6 (MUFU lg2/ex2/rcp in P(0)), so its cdf tops
-// out anywhere in 1 +- 4e-6.  Stretching u by more than that makes the error one-sided: a u above the
-// top of the computed cdf (probability ~8e-6) is detected when the search freezes and the count is
-// redrawn, so the accepted draws follow pmf/(1+eps) renormalised, i.e. the exact pmf, and no part of
-// the upper tail is cut off.
-constexpr float kInversionStretch = 8.0e-6f;
-// cdf(0) - u with u = w 2^-32 (1 + stretch) in [0, 1 + 8e-6): no half-step offset (u = 0 is harmless for
-// an inversion, X = 0), so the conversion and the subtraction are one I2FP and one FFMA
-__device__ __forceinline__ float cdf0_minus_u(float p0, uint32_t w) {
-  return fmaf((float)w, -2.3283064365386963e-10f * (1.0f + kInversionStretch), p0);
+// The uniform of the NB cdf inversion, stretched to [0, 1 + 2^-15).  The fp32 pmf of the inversion
+// is exact up to a common factor 1 + eps (MUFU lg2/ex2/rcp and the rounding of log2 P(0); |eps| <=
+// 1.5e-5 for the parameters routed to the inversion, see nb_route_inversion), so its cdf tops out
+// anywhere in 1 +- 1.5e-5.  Stretching u by more than that makes the error one-sided: a u above the top
+// of the computed cdf is detected (in the fp64 tail path, invert_tail_f64) and the count is redrawn,
+// so the accepted draws follow pmf (1+eps) renormalised, i.e. the exact pmf, and no part of the
+// upper tail is cut off.
+constexpr float kInversionStretch = 3.0517578125e-5f;                    // 2^-15
+// Philox words whose fp32 image is >= 2^32 (1 - 2^-14) (the top 6.1e-5 of the uniforms) are not
+// decided by the fp32 search: their count is inverted in fp64 with 32 more random bits
+// (invert_tail_f64).  The route depends on the uniform alone.
+constexpr float kTailWord = 4294705152.0f;                               // 2^32 - 2^18
+// cdf(0) - u with u = w 2^-32 (1 + stretch): no half-step offset (u = 0 is harmless for an
+// inversion, X = 0), so the subtraction is one FFMA on the converted Philox word
+__device__ __forceinline__ float cdf0_minus_u(float p0, float w_as_float) {
+  return fmaf(w_as_float, -2.3283064365386963e-10f * (1.0f + kInversionStretch), p0);
 }
 // 53-bit double in [0,1) exactly as numpy's legacy random_sample builds it
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
@@ -101,6 +108,44 @@ __device__ __forceinline__ double normal_f64(uint4 r) {
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// ---------------------------------------------------------------------------
+// NB parameterisation of the inversion path, fp32 (count_model.py:156-161 in the gamma-Poisson
+// form): theta = alpha mu + beta - 1 (gamma scale), r = mu/theta (gamma shape, scipy's n),
+// q = theta/(1+theta) = 1 - p, a = q r, log2 P(0) = -r log2(1+theta).  ONE definition, used by
+// the draw kernel's head, its fp64 tail path and the parity hook pst_nb_params_f32.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float nb_shape(float mu, float th) { return mu * rcp_fast(th); }   // r = mu/theta
+__device__ __forceinline__ void nb_inversion_params_fast(float mu, float th, float &q, float &a, float &e2) {
+  const float t1 = 1.0f + th;
+  const float r = nb_shape(mu, th);
+  q = th * rcp_fast(t1);
+  a = q * r;
+  e2 = -r * lg2_fast(t1);                      // log2 P(0) = -r log2(1+theta)
+}
+// theta -> 0 (Poisson limit): log2 P(0) = -mu log2(e) log1p(theta)/theta by series, exact as theta -> 0
+constexpr float kSmallTheta = 0.1f;
+__device__ __forceinline__ float nb_log2p0_small_theta(float mu, float th) {
+  const float ser = fmaf(th, fmaf(th, fmaf(th, fmaf(th, fmaf(th, fmaf(th, 0.1428571429f, -0.1666666667f), 0.2f),
+                                                  -0.25f), 0.3333333333f), -0.5f), 1.0f);
+  return -1.4426950409f * mu * ser;
+}
+__device__ __forceinline__ void nb_inversion_params(float mu, float th, float &q, float &a, float &e2) {
+  nb_inversion_params_fast(mu, th, q, a, e2);
+  if (th < kSmallTheta) e2 = nb_log2p0_small_theta(mu, th);
+}
+// Which counts the hybrid sampler inverts (the rest goes to the gamma-Poisson mixture): a function of
+// the parameters only.  mean <= 32 and sd <= 20 bound the length of a search; shape r <= 48 (or the
+// small-theta series) bounds the error of log2 P(0): r |d lg2| <= 48 (2^-22 + 2^-24/ln 2) = 1.6e-5.
+constexpr float kInvMuMax = 32.0f, kInvVarMax = 400.0f, kInvShapeMax = 48.0f;
+__device__ __forceinline__ bool nb_shape_ok(float th, float q, float a) {     // r = a/q <= 48, or the series
+  return (a <= kInvShapeMax * q) || (th < kSmallTheta);
+}
+__device__ __forceinline__ bool nb_route_inversion(float mu, float th, float q, float a, float mu_max = kInvMuMax,
+                                                   float var_max = kInvVarMax) {
+  return (mu > 0.f) && (mu <= mu_max) && (th > 0.f) && (mu * (1.0f + th) <= var_max) &&
+         nb_shape_ok(th, q, a);                            // comparisons are false on NaN
+}
 
 // L2 residency hints: the means table is re-read by every cell (keep), X is written once (stream)
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {

@@ -138,31 +138,43 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   return MixResult{k, MIX_DONE};
 }
 
-// Rare path of the inversion (about 1e-5 of the inverted counts).  The fp32 pmf is exact up to a
-// common factor 1 + eps (|eps| up to ~4e-6, from the MUFU lg2 / ex2 / rcp in P(0)); the uniform is
-// stretched to (0, 1 + 8e-6] (u01_inversion) so that the computed cdf always tops out below the
-// largest u.  A uniform above the top never finds its crossing: the search freezes far out in the
-// tail and the count is redrawn here from the same distribution with a fresh uniform (block
-// 0xffffffff of the count's own Philox stream, which the mixture never reaches).  Accepted and
-// redrawn counts together follow the exact pmf; without this the lost mass would pile up at the
-// 1 - 3e-8 quantile (undershoot) or the top eps quantile would never be produced (overshoot).
-//   a = q r, q = theta/(1+theta):  P(0) = (1-q)^r,  log2 P(0) = a log2(1-q)/q
-__device__ __noinline__ int redraw_inversion(float a, float q, uint32_t key0, uint32_t key1, uint32_t gene,
-                                             int64_t cell, int kmax) {
-  const uint32_t c1 = (uint32_t)cell, c2 = (TAG_COUNT << 16) | (uint32_t)((uint64_t)cell >> 32);
-  const uint4 w = philox_s(key0, key1, gene, c1, c2, 0xffffffffu);
-  const float u = u01(w.x);
-  const float l = (q < 0.05f)       // log2(1-q)/q, by series towards the Poisson limit q -> 0
-      ? -1.4426950409f * fmaf(q, fmaf(q, fmaf(q, fmaf(q, 0.2f, 0.25f), 0.3333333333f), 0.5f), 1.0f)
-      : log2f(1.0f - q) / q;
-  const float mu = a / (1.0f - q);
-  float p = exp2f(a * l), cdf = p;
+// Far upper tail of the inversion (the top 2^-14 of the uniforms, listed by the draw kernel by the
+// Philox word alone and finished by tail_fix_kernel) and the redraws.  fp32 cannot resolve the cdf next to 1 (spacing 6e-8), so these counts are
+// inverted in fp64 with a 64-bit uniform: the head's word w refined by 32 more random bits,
+// U = (w + (w2 + 1/2) 2^-32) 2^-32, stretched like the fp32 uniform (u = U (1 + 2^-15)).  The pmf
+// starts from the SAME fp32 P(0), a, q as the head (nb_inversion_params), so the fp32 and fp64 parts
+// of the cdf join up to fp32 rounding where the route switches, and the cdf computed here tops out at
+// T = 1 + eps like the head's.  u >= T (probability ~2^-15) has no crossing: the count is redrawn
+// with a fresh 64-bit uniform over the whole range, so that accepted draws follow pmf (1+eps) / T,
+// the exact pmf.  Random words: blocks 0xffffffff, 0xfffffffe, ... of the count's own (cell, gene)
+// stream, which the mixture (blocks 2a, 2a+1, a <= 62) never reaches.
+constexpr int HY_KMAX64 = 1 << 16;
+__device__ __forceinline__ int invert_tail_f64(float mu, float th, uint32_t key0, uint32_t key1, uint32_t gene,
+                                            int64_t cell) {
+  float qf, af, e2;
+  nb_inversion_params(mu, th, qf, af, e2);
+  const double p0 = (double)ex2_fast(e2), a = (double)af, q = (double)qf;
+  const uint32_t c1 = (uint32_t)cell, chi = (uint32_t)((uint64_t)cell >> 32);
+  const uint4 wq = philox_s(key0, key1, gene >> 2, c1, (TAG_QUAD << 16) | chi, 0u);   // the head's block
+  const uint32_t j = gene & 3u;
+  const uint32_t w = j == 0 ? wq.x : j == 1 ? wq.y : j == 2 ? wq.z : wq.w;
+  const double stretch = 1.0 + (double)kInversionStretch;
   int k = 0;
-  while (cdf < u && k < kmax) {
-    p *= fmaf(q, (float)k, a) / (float)(k + 1);
-    cdf += p;
-    ++k;
-    if (p <= 2.0e-8f && (float)k > mu) break;      // frozen again (probability ~1e-12): keep k
+  for (uint32_t attempt = 0; attempt < 16u; ++attempt) {
+    const uint4 wt = philox_s(key0, key1, gene, c1, (TAG_COUNT << 16) | chi, 0xffffffffu - attempt);
+    const double hi = attempt == 0 ? (double)w : (double)wt.y;
+    const double u = (hi + ((double)wt.x + 0.5) * 2.3283064365386963e-10) * 2.3283064365386963e-10 * stretch;
+    double p = p0, cdf = p0;
+    bool above = false;
+    k = 0;
+    while (cdf < u) {
+      // past the mode with a term that cannot move the cdf any more: u lies above the top T
+      if (k >= HY_KMAX64 || (p < 1e-18 && (float)k > mu)) { above = true; break; }
+      p *= fma(q, (double)k, a) / (double)(k + 1);             // P(k+1) = P(k) (a + q k)/(k+1)
+      cdf += p;
+      ++k;
+    }
+    if (!above) break;
   }
   return k;
 }
@@ -197,16 +209,13 @@ constexpr int HY_WARPS = 4;                  // warps per CTA
 constexpr int HY_THREADS = HY_WARPS * 32;
 constexpr int HY_QCAP = 160;                 // 31 carried + 128 new entries, rounded up
 constexpr int HY_KMAX = 2048;                // hard bound on inversion terms
-constexpr float HY_FROZEN = 2.0f;            // cdf(k)-u sentinel (natural values are <= 1): the search froze below u
 #ifndef HY_STAGE2
 #define HY_STAGE2 24                         // unrolled terms at the start of the tail
 #endif
-constexpr float HY_MU_MAX = 32.0f, HY_VAR_MAX = 400.0f;   // route: mean <= 32 and sd <= 20
+constexpr float HY_MU_MAX = kInvMuMax, HY_VAR_MAX = kInvVarMax;   // route: mean <= 32 and sd <= 20 (nb_route_inversion)
 constexpr int HY_KFIX = 10;                                  // unrolled head terms
-// The tail's frozen-cdf guard (pp <= 2e-8 -> stop counting) assumes it can only trigger past the
-// mode: for every routed (mu, theta) the pmf at k >= HY_KFIX-1 is above 2e-8 until the mode.  The
-// smallest such value is Poisson(32) at k = 9: 1.2e-6.  Larger HY_MU_MAX would break that.
-static_assert(HY_MU_MAX <= 32.0f && HY_KFIX >= 10, "frozen-cdf guard needs P(k>=KFIX-1) > 2e-8 before the mode");
+// mean <= 32 keeps P(0) >= e^-32 (|log2 P(0)| <= 46, t_k = P(k) k! inside the fp32 range)
+static_assert(HY_MU_MAX <= 32.0f, "the t_k form and the error bound of log2 P(0) assume mean <= 32");
 
 // 1/(k+1) for the open-ended part of the search drain, k = K_TAIL0 + j: read four at a time from the
 // constant bank with a warp-uniform index instead of one MUFU.RCP per term
@@ -218,6 +227,10 @@ __host__ __device__ constexpr RcpTail make_rcp_tail() {
   return t;
 }
 __constant__ __align__(16) RcpTail c_rcp_tail = make_rcp_tail();
+
+// work-scheduler words of pst_draw_counts: [slot][0] next chunk, [slot][1] warps that have left; one
+// slot per (device, stream), see sched_slot().  Zero between launches (the last warp rearms them).
+__device__ unsigned int g_sched[PST_SCHED_SLOTS][2];
 
 struct HyWarpQueues {
   float4 se[HY_QCAP];       // inversion tail: t = P(k) k! at k = KFIX-1, cdf(k)-u, a, q
@@ -247,7 +260,8 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
                           const float *__restrict__ scaling, const float *__restrict__ alpha,
                           const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
                           int32_t *__restrict__ X, uint32_t ldx, uint32_t *__restrict__ flags,
-                          const int32_t *__restrict__ cell_order, float mu_max_arg, float var_max_arg) {
+                          const int32_t *__restrict__ cell_order, float mu_max_arg, float var_max_arg,
+                          int sched, uint32_t *__restrict__ tail, uint32_t tail_cap) {
 #ifdef PST_DEV_KNOBS
   const float mu_max = mu_max_arg, var_max = var_max_arg;
 #else
@@ -302,13 +316,10 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
         cn += (int)(__float_as_uint(dd) >> 31);
         ak += qq;
       }
-      // u beyond what the fp32 cdf can reach: stop counting, mark the entry for the redraw
-      dd = (pp <= 2.0e-8f && dd < 0.f) ? HY_FROZEN : dd;
     }
+    // every u handled here lies below 1 - 2^-15 < T, the top of the computed cdf, and cdf - u is
+    // accumulated (exact near the crossing), so each search ends; HY_KMAX only bounds the loop
     const int2 w = act ? wq.sw[e] : make_int2(0, 0);
-    if (__any_sync(0xffffffffu, dd == HY_FROZEN)) {          // about one batch in 10^3
-      if (dd == HY_FROZEN) cn = redraw_inversion(aa, qq, key0, key1, (uint32_t)w.y, cell0 + w.x, HY_KMAX);
-    }
     if (act) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
   };
   // one mixture step for up to 32 queued entries; rejected entries go back to the queue (returns
@@ -369,11 +380,11 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     }
   };
 
-  // chunks are handed out dynamically (flags[1] is the next-chunk counter): warps whose
+  // chunks are handed out dynamically (g_sched[sched][0] is the next-chunk counter): warps whose
   // queues drain more often simply take fewer chunks
   for (;;) {
     unsigned claimed = 0;
-    if (lane == 0) claimed = atomicAdd(&flags[1], 1u);
+    if (lane == 0) claimed = atomicAdd(&g_sched[sched][0], 1u);
     claimed = __shfl_sync(0xffffffffu, claimed, 0);
     if ((int64_t)claimed >= n_chunks) break;                  // no work left
     const uint32_t cgroup = claimed / n_strips;
@@ -401,9 +412,11 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     }
     // theta = alpha*mu + (beta-1) >= beta-1 when alpha, mu >= 0, so the Poisson-limit series below can
     // only be needed in chunks where some gene has beta-1 < 0.1 (or a negative alpha): one vote per chunk
-    const bool chunk_small_theta = __any_sync(
-        0xffffffffu, fminf(fminf(bm[0], bm[1]), fminf(bm[2], bm[3])) < 0.1f ||
-                         fminf(fminf(al[0], al[1]), fminf(al[2], al[3])) < 0.f);
+    const float al_min = fminf(fminf(al[0], al[1]), fminf(al[2], al[3]));
+    const float bm_min = fminf(fminf(bm[0], bm[1]), fminf(bm[2], bm[3]));
+    const bool chunk_small_theta = __any_sync(0xffffffffu, bm_min < kSmallTheta || al_min < 0.f);
+    // gamma shape r = mu/theta <= 1/alpha when beta-1 >= 0: shapes above kInvShapeMax need a tiny alpha
+    const bool chunk_big_shape = __any_sync(0xffffffffu, !(al_min * kInvShapeMax >= 1.001f) || bm_min < 0.f);
     // Per-cell metadata (cell id, tree row, library size) is the same for every lane: lane l
     // loads it for cell (group*32 + l) with one coalesced request per 32 cells and the loop
     // broadcasts it with shuffles.  The means quad of the next cell is prefetched: register load
@@ -455,34 +468,49 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       const int64_t gcell = cell0 + cell;
       const uint4 rnd = philox(key, quad, (uint32_t)gcell,
                                (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
-      const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+      float fw[4] = {(float)rnd.x, (float)rnd.y, (float)rnd.z, (float)rnd.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         mu[j] = m[j] * s;
         th[j] = fmaf(al[j], mu[j], bm[j]);
-        const float t1 = 1.0f + th[j];
-        const float r = mu[j] * rcp_fast(th[j]);
-        q[j] = th[j] * rcp_fast(t1);
-        a[j] = q[j] * r;
-        e2[j] = -r * lg2_fast(t1);                 // log2 P(0) = -r log2(1+theta)
-        // inversion only for small mean and variance; comparisons are false on NaN
-        small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * t1 <= var_max);
+        nb_inversion_params_fast(mu[j], th[j], q[j], a[j], e2[j]);
+        // inversion only for small mean and variance (nb_route_inversion without the shape test)
+        small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * (1.0f + th[j]) <= var_max);
       }
       // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
-      if (chunk_small_theta && fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < 0.1f) {
+      if (chunk_small_theta && fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < kSmallTheta) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e2[j] = (th[j] < kSmallTheta) ? nb_log2p0_small_theta(mu[j], th[j]) : e2[j];
+      }
+      // large gamma shapes (nearly Poisson genes with theta >= 0.1) go to the mixture: r log2(1+theta)
+      // would carry too large an error.  r <= 1/alpha, so only chunks with a tiny alpha can have them
+      if (chunk_big_shape) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) small[j] = small[j] && nb_shape_ok(th[j], q[j], a[j]);
+      }
+      // The top 2^-14 of the uniforms is not decided in fp32: those counts (chosen by the Philox word
+      // alone) are appended with their parameters to the launch's tail list and inverted in fp64 by
+      // tail_fix_kernel; the head sees them as decided (their word is replaced by one that gives
+      // cdf(0) - u > 0: count 0 until the fix-up writes it)
+      if (fmaxf(fmaxf(fw[0], fw[1]), fmaxf(fw[2], fw[3])) >= kTailWord) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float x = th[j];
-          const float ser = fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 0.1428571429f, -0.1666666667f), 0.2f),
-                                                          -0.25f), 0.3333333333f), -0.5f), 1.0f);
-          e2[j] = (x < 0.1f) ? -1.4426950409f * mu[j] * ser : e2[j];
+          if (small[j] && (fw[j] >= kTailWord) && (VEC || g0 + j < G)) {
+            const unsigned slot = atomicAdd(tail, 1u);
+            if (slot < tail_cap)
+              reinterpret_cast<uint4 *>(tail + 4)[slot] =
+                  make_uint4((uint32_t)cell, g0 + j, __float_as_uint(mu[j]), __float_as_uint(th[j]));
+            else
+              flag |= PST_FLAG_SCRATCH;
+            fw[j] = -4.0e9f;
+          }
         }
       }
       // P(0) and cdf(0) - u for the inversion lanes
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         t[j] = ex2_fast(e2[j]);                     // P(0)
-        d[j] = cdf0_minus_u(t[j], rw[j]);           // cdf(0) - u, one FFMA
+        d[j] = cdf0_minus_u(t[j], fw[j]);           // cdf(0) - u, one FFMA
         cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
       }
       }  // !ALL_MIX
@@ -560,8 +588,41 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   if (flag) atomicOr(flags, flag);
   // the last warp to leave rearms the scheduler words for the next launch
   if (lane == 0) {
-    const unsigned done = atomicAdd(&flags[2], 1u);
-    if (done == (unsigned)n_warps - 1u) { flags[1] = 0u; flags[2] = 0u; __threadfence(); }
+    const unsigned done = atomicAdd(&g_sched[sched][1], 1u);
+    if (done == (unsigned)n_warps - 1u) { g_sched[sched][0] = 0u; g_sched[sched][1] = 0u; __threadfence(); }
+  }
+}
+
+// Parity hook: the fp32 parameterisation exactly as the draw kernel computes it (same __device__
+// functions), one element per (mu, alpha, beta-1) triple.
+__global__ void nb_params_f32_kernel(const float *__restrict__ mu, const float *__restrict__ alpha,
+                                     const float *__restrict__ beta_m1, int64_t n, float *__restrict__ out_theta,
+                                     float *__restrict__ out_r, float *__restrict__ out_q, float *__restrict__ out_a,
+                                     float *__restrict__ out_log2p0, int32_t *__restrict__ out_route) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mu[i];
+    const float th = fmaf(alpha[i], m, beta_m1[i]);
+    float q, a, e2;
+    nb_inversion_params(m, th, q, a, e2);
+    out_theta[i] = th;
+    out_r[i] = nb_shape(m, th);
+    out_q[i] = q;
+    out_a[i] = a;
+    out_log2p0[i] = e2;
+    out_route[i] = !nb_domain_ok(m, th) ? PST_ROUTE_DOMAIN_ERROR
+                   : nb_route_inversion(m, th, q, a) ? PST_ROUTE_INVERSION : PST_ROUTE_MIXTURE;
+  }
+}
+
+// The counts the draw kernel listed for the fp64 tail path, one thread each.  tail[0] = number of
+// entries, entries (cell, gene, mu, theta) from word 4 on.
+__global__ void tail_fix_kernel(const __grid_constant__ PhiloxKey key, const uint32_t *__restrict__ tail,
+                                uint32_t tail_cap, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx) {
+  const uint32_t n = min(tail[0], tail_cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 e = reinterpret_cast<const uint4 *>(tail + 4)[i];
+    X[(uint64_t)e.x * ldx + e.y] =
+        invert_tail_f64(__uint_as_float(e.z), __uint_as_float(e.w), key.k0[0], key.k1[0], e.y, cell0 + (int64_t)e.x);
   }
 }
 
@@ -729,7 +790,7 @@ extern "C" int pst_count_stats(const int32_t *X, int64_t n, int64_t G, int64_t l
   const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
   const int64_t n_chunks = ((n + ST_ROWS - 1) / ST_ROWS) * ((((G + 3) / 4) + 31) / 32);
   const int64_t need = (n_chunks + 7) / 8;                        // 8 warps per CTA
-  const unsigned blocks = (unsigned)std::min<int64_t>(need, (int64_t)kNumSM * 2);   // 2 CTAs of 8 warps per SM
+  const unsigned blocks = (unsigned)std::min<int64_t>(need, (int64_t)num_sm() * 2);   // 2 CTAs of 8 warps per SM
   typedef unsigned long long ull;
   if (vec)
     count_stats_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -750,7 +811,7 @@ extern "C" int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(bins, 0, sizeof(uint32_t) * (size_t)P, st);
   if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "memset failed"); }
-  const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)kNumSM * 8);
+  const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sm() * 8);
   row_histogram_kernel<<<g, 256, 0, st>>>(row_of_cell, n, P, bins);
   int rc = check_launch(fn);
   if (rc) return rc;
@@ -762,11 +823,33 @@ extern "C" int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int
 }
 
 
+extern "C" int pst_nb_params_f32(const float *mu, const float *alpha, const float *beta_m1, int64_t n,
+                                 float *out_theta, float *out_r, float *out_q, float *out_a, float *out_log2p0,
+                                 int32_t *out_route, void *stream) {
+  const char *fn = "pst_nb_params_f32";
+  PST_REQUIRE(n >= 0, fn, "negative size");
+  if (n == 0) return 0;
+  PST_REQUIRE(mu && alpha && beta_m1 && out_theta && out_r && out_q && out_a && out_log2p0 && out_route, fn,
+              "null pointer");
+  const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sm() * 8);
+  nb_params_f32_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(mu, alpha, beta_m1, n, out_theta, out_r, out_q, out_a,
+                                                            out_log2p0, out_route);
+  return check_launch(fn);
+}
+
+extern "C" int64_t pst_draw_scratch_words(int64_t n, int64_t G) {
+  if (n <= 0 || G <= 0) return 4;
+  // 4 header words + 4 words per listed count; twice the expected 2^-14 n G entries plus 1024: a list
+  // that does not fit would be a > 30 sigma event
+  const double expect = (double)n * (double)G / 16384.0;
+  return 4 + 4 * ((int64_t)(2.0 * expect) + 1024);
+}
+
 extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const int32_t *row_of_cell,
                                const float *scaling, const float *alpha, const float *beta_m1,
                                uint64_t seed, int64_t cell0, int64_t n, int32_t *X, int64_t ldx,
                                uint32_t *flags, int32_t sampler, const int32_t *cell_order,
-                               void *stream) {
+                               uint32_t *scratch, int64_t scratch_words, void *stream) {
   const char *fn = "pst_draw_counts";
   PST_REQUIRE(P >= 0 && G >= 0 && n >= 0 && cell0 >= 0, fn, "negative size");
   PST_REQUIRE(ldx >= G, fn, "ldx < G");
@@ -799,16 +882,28 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
     const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * ((Q + 31) / 32);
     PST_REQUIRE(n_chunks < ((int64_t)1 << 31), fn, "too many work chunks in one call (chunk the cells)");
     const int64_t need = (n_chunks + HY_WARPS - 1) / HY_WARPS;
-    const int64_t cap = (int64_t)kNumSM * ctas_per_sm;    // persistent CTAs of 4 warps, one wave
+    const int64_t cap = (int64_t)num_sm() * ctas_per_sm;    // persistent CTAs of 4 warps, one wave
+    const int slot = sched_slot(stream);
+    PST_REQUIRE(slot >= 0, fn, "more than 4096 distinct streams have called pst_draw_counts on this device");
+    // tail list of the hybrid sampler: scratch[0] = entries appended, entries from word 4 on
+    uint32_t tail_cap = 0;
+    if (sampler == PST_SAMPLER_HYBRID) {
+      PST_REQUIRE(scratch && scratch_words >= pst_draw_scratch_words(n, G), fn,
+                  "the hybrid sampler needs pst_draw_scratch_words(n, G) words of scratch");
+      PST_REQUIRE((uintptr_t)scratch % 16 == 0, fn, "scratch must be 16-byte aligned");
+      tail_cap = (uint32_t)std::min<int64_t>((scratch_words - 4) / 4, (int64_t)0xffffffff);
+      const cudaError_t e = cudaMemsetAsync(scratch, 0, 16, st);
+      if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "memset failed"); }
+    }
     const unsigned hb = (unsigned)(need < cap ? need : cap);
 #define PST_LAUNCH_HYBRID(KF, MIX)                                                                         \
     do {                                                                                                   \
       if (vec) draw_counts_hybrid_kernel<KF, true, MIX><<<hb, HY_THREADS, 0, st>>>(                        \
           PhiloxKey(seed), means, (uint32_t)P, (uint32_t)G, (uint32_t)Q, row_of_cell, scaling, alpha,      \
-          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max);                        \
+          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max, slot, scratch, tail_cap);                  \
       else draw_counts_hybrid_kernel<KF, false, MIX><<<hb, HY_THREADS, 0, st>>>(                           \
           PhiloxKey(seed), means, (uint32_t)P, (uint32_t)G, (uint32_t)Q, row_of_cell, scaling, alpha,      \
-          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max);                        \
+          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max, slot, scratch, tail_cap);                  \
     } while (0)
     if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
       PST_LAUNCH_HYBRID(HY_KFIX, true);
@@ -825,6 +920,12 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
     PST_LAUNCH_HYBRID(HY_KFIX, false);
 #endif
 #undef PST_LAUNCH_HYBRID
+    const int rc = check_launch(fn);
+    if (rc) return rc;
+    // expected entries: 2^-14 of the inverted counts; one thread each, grid-stride beyond that
+    const int64_t expect = (int64_t)((double)n * (double)G / 16384.0) + 256;
+    const unsigned tb = (unsigned)std::min<int64_t>((expect + 127) / 128, (int64_t)num_sm() * 16);
+    tail_fix_kernel<<<tb, 128, 0, st>>>(PhiloxKey(seed), scratch, tail_cap, cell0, X, (uint32_t)ldx);
     return check_launch(fn);
   }
 }

@@ -145,7 +145,7 @@ narrow_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx, 
 }
 
 inline unsigned stream_grid(int64_t threads) {
-  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, (int64_t)kNumSM * 16));
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, (int64_t)num_sm() * 16));
 }
 
 }  // namespace
@@ -165,7 +165,7 @@ extern "C" int pst_transform_counts(const int32_t *X, int64_t n, int64_t G, int6
   const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
                    ((uintptr_t)out % 16 == 0);
   const int64_t qblocks = std::min<int64_t>((((G + 3) / 4) + 255) / 256, 64);
-  const int64_t yblocks = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)kNumSM * 16 + qblocks - 1) / qblocks));
+  const int64_t yblocks = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)num_sm() * 16 + qblocks - 1) / qblocks));
   const dim3 grid((unsigned)qblocks, (unsigned)yblocks);
   cudaStream_t st = (cudaStream_t)stream;
 #define PST_LAUNCH_TRANSFORM(M)                                                                  \
@@ -207,7 +207,7 @@ extern "C" int pst_narrow_counts(const int32_t *X, int64_t n, int64_t G, int64_t
   const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
                    ((uintptr_t)out % (4 * obytes) == 0);
   const int64_t qblocks = std::min<int64_t>((((G + 3) / 4) + 255) / 256, 64);
-  const int64_t yblocks = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)kNumSM * 16 + qblocks - 1) / qblocks));
+  const int64_t yblocks = std::max<int64_t>(1, std::min<int64_t>(n, ((int64_t)num_sm() * 16 + qblocks - 1) / qblocks));
   const dim3 grid((unsigned)qblocks, (unsigned)yblocks);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long *cnt = (unsigned long long *)ovf_count;

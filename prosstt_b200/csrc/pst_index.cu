@@ -2,12 +2,49 @@
 // Reference behaviour: prosstt/simulation.py:319-548 (sample_density, sample_pseudotime_series,
 // draw_times, sample_whole_tree), prosstt/sim_utils.py:342-403 (pick_branches/pick_branch),
 // :473-498 (calc_scalings).  fp64 + integers; maps are bit-exact given the same uniforms/normals.
+#include <map>
+#include <mutex>
+#include <utility>
 #include "pst_common.cuh"
 
 namespace pst {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+
+int num_sm() {
+  static std::atomic<int> cached[64];                 // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 148;                                        // B200: 2 dies x 74 SMs
+    }
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+// pst_draw_counts hands out its work chunks through a device-side counter.  The counters live in a
+// library-owned __device__ array (one instance per GPU); every (device, stream) pair gets its own
+// slot, so launches on different streams never share one and launches on one stream are ordered.
+int sched_slot(void *stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, void *>, int> slots;
+  static int next_slot[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = 0; }
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair(dev, stream);
+  const auto it = slots.find(key);
+  if (it != slots.end()) return it->second;
+  if (next_slot[dev] >= PST_SCHED_SLOTS) return -1;
+  const int s = next_slot[dev]++;
+  slots[key] = s;
+  return s;
+}
 
 int fail_arg(const char *fn, const char *what) {
   snprintf(g_err, sizeof(g_err), "%s: %s", fn, what);
@@ -233,7 +270,7 @@ __global__ void nb_params_kernel(const double *__restrict__ alpha, const double 
 
 static inline unsigned grid_for(int64_t n) {
   const int64_t b = (n + 255) / 256;
-  const int64_t cap = (int64_t)kNumSM * 8;
+  const int64_t cap = (int64_t)num_sm() * 8;
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 

@@ -254,7 +254,7 @@ extern "C" int pst_rel_means(const double *W, const double *H, const double *gen
   PST_REQUIRE(K <= 1024, fn, "K > 1024 programs not supported");
   const int64_t gx = (G + RM_THREADS - 1) / RM_THREADS;
   // enough row chunks for ~4 CTAs per SM, each a multiple of the register tile
-  int64_t want_y = (4 * kNumSM + gx - 1) / gx;
+  int64_t want_y = (4 * num_sm() + gx - 1) / gx;
   int64_t rows_per_block = (nrows + want_y - 1) / want_y;
   rows_per_block = ((rows_per_block + RM_RT - 1) / RM_RT) * RM_RT;
   const int64_t gy = (nrows + rows_per_block - 1) / rows_per_block;
@@ -281,7 +281,7 @@ extern "C" int pst_f64_to_f32(const double *in, int64_t n, double min_positive, 
   PST_REQUIRE(n >= 0, fn, "negative size");
   if (n == 0) return 0;
   PST_REQUIRE(in && out, fn, "null pointer");
-  const int64_t blocks = min((n + 255) / 256, (int64_t)kNumSM * 16);
+  const int64_t blocks = min((n + 255) / 256, (int64_t)num_sm() * 16);
   f64_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, n, min_positive, out);
   return check_launch(fn);
 }

@@ -170,6 +170,8 @@ def raise_flags(word):
     if word & nat.FLAG_DOMAIN:
         raise ValueError("Domain error in arguments. The mean expression must be positive "
                          "and alpha*mean + beta must exceed 1 for every cell and gene.")
+    if word & nat.FLAG_SCRATCH:
+        raise RuntimeError("the tail list of pst_draw_counts overflowed (scratch too small)")
     if word & nat.FLAG_CLAMPED:
         raise OverflowError("a sampled count exceeded the int32 range")
 
@@ -184,9 +186,9 @@ class CountEngine(object):
         self.means = means_table(tree, tables, dev)
         self.alpha, self.beta_m1 = gene_params(alpha, beta, self.G, dev)
         self.sampler = nat.SAMPLERS[sampler]
-        self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # status + scheduler scratch
+        self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # status word (+3 reserved)
         self.group_rows = not os.environ.get("PST_NO_GROUP")    # developer switch
-        self._order = self._bins = None
+        self._order = self._bins = self._scratch = None
         self.overflow = None                                    # filled by draw_to_host (uint16 format)
 
     def draw(self, rows, scaling32, seed, cell0, out=None):
@@ -205,10 +207,17 @@ class CountEngine(object):
             order = self._order[:n]
             nat.call("pst_group_cells_by_row", nat.ptr(rows), n, self.P, nat.ptr(self._bins),
                      nat.ptr(order), st)
+        scratch, words = None, 0
+        if self.sampler == nat.SAMPLER_HYBRID:
+            # list of the counts that the fix-up kernel inverts in fp64 (top 2^-14 of the uniforms)
+            words = int(nat.load().pst_draw_scratch_words(n, self.G))
+            if self._scratch is None or self._scratch.numel() < words:
+                self._scratch = torch.empty(words, dtype=torch.int32, device=self.dev)
+            scratch = self._scratch
         nat.call("pst_draw_counts", nat.ptr(self.means), self.P, self.G, nat.ptr(rows),
                  nat.ptr(scaling32), nat.ptr(self.alpha), nat.ptr(self.beta_m1),
                  seed, int(cell0), n, out.data_ptr(), out.stride(0) if n else self.G,
-                 nat.ptr(self.flags), self.sampler, order, st)
+                 nat.ptr(self.flags), self.sampler, order, scratch, words, st)
         return out
 
     def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=None):

@@ -16,8 +16,10 @@ from prosstt_b200.device import CountEngine, TreeTables, choice_cdf
 
 
 class DensitySession(object):
-    def __init__(self, tree, alpha, beta, cells, first=0, device=None, sampler="gamma_poisson",
+    def __init__(self, tree, alpha, beta, cells, first=0, device=None, sampler=None,
                  scale=True, scale_mean=0.0, scale_v=0.7, resident_output=True):
+        if sampler is None:                       # same default as simulation.sample_density
+            from prosstt_b200.simulation import DEFAULT_SAMPLER as sampler
         self.dev = nat.device(device)
         self.tree = tree
         self.n, self.first = int(cells), int(first)

@@ -162,7 +162,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(nat.declared_symbols())
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.pst_abi_version() == 1
+    assert lib.pst_abi_version() == 2
     assert lib.pst_launch_count() == 0
 
 

@@ -21,7 +21,10 @@ ap.add_argument("--chunk", type=int, default=50_000_000)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 regimes = [(0.3, 0.3, 2.0), (1.8, 0.2, 2.0), (6.0, 0.25, 1.6), (14.0, 0.1, 2.5), (31.9, 0.05, 1.5),
-           (32.1, 0.05, 1.5), (20.0, 0.9, 2.0), (150.0, 0.3, 2.0)]
+           (32.1, 0.05, 1.5), (20.0, 0.9, 2.0), (150.0, 0.3, 2.0),
+           # round 2: strongly over-dispersed corner (theta = 101), large gamma shape on the inversion route
+           # (r = 37.5), the small-theta series with a large shape (r = 91), and a shape beyond the cap (mixture)
+           (1.0, 100.0, 2.0), (30.0, 0.02, 1.2), (5.0, 0.001, 1.05), (30.0, 0.001, 1.3)]
 mu = np.array([r[0] for r in regimes]); alpha = np.array([r[1] for r in regimes]); beta = np.array([r[2] for r in regimes])
 G = len(regimes)
 t = ptree.Tree(topology=[["A", "B"]], time={"A": 1, "B": 1}, num_branches=2, branch_points=0, modules=1, G=G)
@@ -70,7 +73,8 @@ for sampler in ("hybrid", "gamma_poisson"):
         big = pmf * N >= 1e5
         dev_rel = np.max(np.abs(obs[big] / (pmf[big] * N) - 1)) if big.any() else float("nan")
         mean = (hist * np.arange(len(hist))).sum() / N
-        print("%-13s mu=%6.1f alpha=%.2f beta=%.1f  N=%.0e  body bins=%3d chi2/dof=%.3f p=%.3g  max rel dev (exp>=1e5)=%.1e"
-              "  mean/mu-1=%+.1e  tail mass obs/exp: sf<1e-6 %.2e/%.2e  sf<1e-7 %.2e/%.2e  max=%d"
+        sig6, sig7 = (t6 - e6) * N / np.sqrt(max(e6 * N, 1)), (t7 - e7) * N / np.sqrt(max(e7 * N, 1))
+        print("%-13s mu=%6.1f alpha=%.3f beta=%.2f  N=%.0e  body bins=%3d chi2/dof=%.3f p=%.3g  max rel dev (exp>=1e5)=%.1e"
+              "  mean/mu-1=%+.1e  tail mass obs/exp: sf<1e-6 %.2e/%.2e (%+.1f sigma)  sf<1e-7 %.2e/%.2e (%+.1f sigma)  max=%d"
               % (sampler, mu[g], alpha[g], beta[g], N, len(e), chi2 / (len(e) - 1), scipy.stats.chi2.sf(chi2, len(e) - 1),
-                 dev_rel, mean / mu[g] - 1, t6, e6, t7, e7, len(hist) - 1), flush=True)
+                 dev_rel, mean / mu[g] - 1, t6, e6, sig6, t7, e7, sig7, len(hist) - 1), flush=True)
