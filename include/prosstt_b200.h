@@ -104,6 +104,17 @@ int pst_rel_means(const double *W, const double *H, const double *gene_scale,
  * (sim_utils.py:145-168, 249-251).  out_count is one int32, caller zeroes it. */
 int pst_pearson_anticorr(const double *A, const double *B, int64_t nrows, int64_t G,
                          int32_t *out_count, void *stream);
+/* The acceptance tests of simulate_lineage (simulation.py:270-272) for a batch of candidate
+ * branches in one launch.  rel is the packed rel table (candidates live in rows behind the P tree
+ * rows).  Candidate i (i < n_slots) owns rows [slot_row[i], slot_row[i]+slot_T[i]): out_slot_max[i]
+ * is max-merged with the maximum of those rows (caller initialises it to -inf) - the
+ * rel_exp_cutoff test.  Pair p compares the first pair_n[p] rows from pair_a[p] and from pair_b[p]:
+ * out_pair_neg[p] (caller zeroes it) receives the number of genes with Pearson r < 0, the
+ * sibling-divergence test (sim_utils.py:145-168, 249-251; same arithmetic as pst_pearson_anticorr). */
+int pst_lineage_checks(const double *rel, int64_t G, int32_t n_slots, const int64_t *slot_row,
+                       const int32_t *slot_T, int32_t n_pairs, const int64_t *pair_a,
+                       const int64_t *pair_b, const int32_t *pair_n, double *out_slot_max,
+                       int32_t *out_pair_neg, void *stream);
 /* fp64 -> fp32 table conversion for means supplied by the user (tree.add_genes).  Positive
  * values below min_positive (pass 1e-30; 0 disables) are raised to it so that a mean that is
  * positive in fp64 never underflows to 0 in the fp32 table (pst_rel_means does the same). */
@@ -246,6 +257,27 @@ int pst_csr_fill(const int32_t *X, int64_t n, int64_t G, int64_t ldx, const int6
 int pst_narrow_counts(const int32_t *X, int64_t n, int64_t G, int64_t ldx, void *out, int64_t ldo,
                       int32_t out_bits, int64_t row0, int64_t *ovf_index, int32_t *ovf_value,
                       int64_t ovf_cap, uint64_t *ovf_count, void *stream);
+
+/* Measurement hook: out[0..n) = value with 128-bit streaming stores (n a multiple of 4, out 16-byte
+ * aligned).  Timed by tools/store_ceiling.py, it gives the write-only HBM ceiling that the count
+ * write of pst_draw_counts is quoted against beside the read+write copy peak. */
+int pst_store_fill(int32_t *out, int64_t n, int32_t value, void *stream);
+
+/* ---- host side of the device->host path (HOST pointers; multi-threaded; no CUDA calls) ------
+ * The count matrix crosses PCIe in a narrow format (pst_narrow_counts) or as int32 into pinned
+ * staging buffers; these routines expand a staged chunk into the caller's matrix - int32, or the
+ * int64 the reference returns (simulation.py:651) - while the GPU samples the next chunk.
+ * dst[i] = (dst type) src[i], i in [0,n): src_bits 8 / 16 (unsigned) or 32 (signed); dst_bits 32 or
+ * 64 (signed).  threads <= 0 uses every hardware thread.  Returns 0, or -1 for an unsupported pair. */
+int pst_host_widen(const void *h_src, int32_t src_bits, void *h_dst, int32_t dst_bits, int64_t n,
+                   int32_t threads);
+/* h_dst[index[i] - base] = value[i] for base <= index[i] < base + n: writes the exact values of the
+ * elements that saturated a narrow format (overflow list of pst_narrow_counts) into a widened chunk. */
+int pst_host_apply_overflow(void *h_dst, int32_t dst_bits, int64_t base, int64_t n,
+                            const int64_t *h_index, const int32_t *h_value, int64_t entries);
+/* sum of the buffer read as uint32 words: the cheapest consumer that touches every byte (the sink
+ * of the streamed many-cells benchmark; a transfer checksum). */
+uint64_t pst_host_checksum(const void *h_src, int64_t bytes, int32_t threads);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "pst_walk_carry": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p]),
     "pst_rel_means": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _i64, _p, _p, _p, _p, _p]),
     "pst_pearson_anticorr": (C.c_int, [_p, _p, _i64, _i64, _p, _p]),
+    "pst_lineage_checks": (C.c_int, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "pst_f64_to_f32": (C.c_int, [_p, _i64, C.c_double, _p, _p]),
     "pst_density_index": (C.c_int, [_p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "pst_times_from_normals": (C.c_int, [_p, _i64, _i32, _p, _p]),
@@ -51,6 +52,10 @@ _SIGNATURES = {
     "pst_count_stats": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "pst_transform_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p]),
     "pst_csr_fill": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "pst_store_fill": (C.c_int, [_p, _i64, _i32, _p]),
+    "pst_host_widen": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32]),
+    "pst_host_apply_overflow": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _i64]),
+    "pst_host_checksum": (_u64, [_p, _i64, _i32]),
     "pst_narrow_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i32, _i64, _p, _p, _i64, _p, _p]),
 }
 

@@ -9,6 +9,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libprosstt_b200.so")
 SOURCES = ["pst_index.cu", "pst_lineage.cu", "pst_counts.cu", "pst_epilogue.cu"]
+HOST_SOURCES = ["pst_host.cpp"]          # host side of the device->host path (threads, no CUDA)
+HOST_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread", "-Wall", "-Wextra"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xptxas=-v", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden"]
@@ -39,6 +41,16 @@ def build(force=False, verbose=False):
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
+        objs.append(obj)
+    cxx = os.environ.get("CXX", "g++")
+    for src in HOST_SOURCES:
+        obj = os.path.join(PKG, "build", src.replace(".cpp", ".o"))
+        cmd = [cxx] + HOST_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("%s failed on %s" % (cxx, src))
         objs.append(obj)
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -80,13 +80,13 @@ __device__ __forceinline__ float u01(uint32_t w) {
 // is exact up to a common factor 1 + eps (MUFU lg2/ex2/rcp and the rounding of log2 P(0); |eps| <=
 // 1.5e-5 for the parameters routed to the inversion, see nb_route_inversion), so its cdf tops out
 // anywhere in 1 +- 1.5e-5.  Stretching u by more than that makes the error one-sided: a u above the top
-// of the computed cdf is detected (in the fp64 tail path, invert_tail_f64) and the count is redrawn,
+// of the computed cdf is detected (in the tail path, invert_tail) and the count is redrawn,
 // so the accepted draws follow pmf (1+eps) renormalised, i.e. the exact pmf, and no part of the
 // upper tail is cut off.
 constexpr float kInversionStretch = 3.0517578125e-5f;                    // 2^-15
 // Philox words whose fp32 image is >= 2^32 (1 - 2^-14) (the top 6.1e-5 of the uniforms) are not
 // decided by the fp32 search: their count is inverted in fp64 with 32 more random bits
-// (invert_tail_f64).  The route depends on the uniform alone.
+// (invert_tail).  The route depends on the uniform alone.
 constexpr float kTailWord = 4294705152.0f;                               // 2^32 - 2^18
 // cdf(0) - u with u = w 2^-32 (1 + stretch): no half-step offset (u = 0 is harmless for an
 // inversion, X = 0), so the subtraction is one FFMA on the converted Philox word

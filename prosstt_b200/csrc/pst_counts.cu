@@ -138,47 +138,6 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   return MixResult{k, MIX_DONE};
 }
 
-// Far upper tail of the inversion (the top 2^-14 of the uniforms, listed by the draw kernel by the
-// Philox word alone and finished by tail_fix_kernel) and the redraws.  fp32 cannot resolve the cdf next to 1 (spacing 6e-8), so these counts are
-// inverted in fp64 with a 64-bit uniform: the head's word w refined by 32 more random bits,
-// U = (w + (w2 + 1/2) 2^-32) 2^-32, stretched like the fp32 uniform (u = U (1 + 2^-15)).  The pmf
-// starts from the SAME fp32 P(0), a, q as the head (nb_inversion_params), so the fp32 and fp64 parts
-// of the cdf join up to fp32 rounding where the route switches, and the cdf computed here tops out at
-// T = 1 + eps like the head's.  u >= T (probability ~2^-15) has no crossing: the count is redrawn
-// with a fresh 64-bit uniform over the whole range, so that accepted draws follow pmf (1+eps) / T,
-// the exact pmf.  Random words: blocks 0xffffffff, 0xfffffffe, ... of the count's own (cell, gene)
-// stream, which the mixture (blocks 2a, 2a+1, a <= 62) never reaches.
-constexpr int HY_KMAX64 = 1 << 16;
-__device__ __forceinline__ int invert_tail_f64(float mu, float th, uint32_t key0, uint32_t key1, uint32_t gene,
-                                            int64_t cell) {
-  float qf, af, e2;
-  nb_inversion_params(mu, th, qf, af, e2);
-  const double p0 = (double)ex2_fast(e2), a = (double)af, q = (double)qf;
-  const uint32_t c1 = (uint32_t)cell, chi = (uint32_t)((uint64_t)cell >> 32);
-  const uint4 wq = philox_s(key0, key1, gene >> 2, c1, (TAG_QUAD << 16) | chi, 0u);   // the head's block
-  const uint32_t j = gene & 3u;
-  const uint32_t w = j == 0 ? wq.x : j == 1 ? wq.y : j == 2 ? wq.z : wq.w;
-  const double stretch = 1.0 + (double)kInversionStretch;
-  int k = 0;
-  for (uint32_t attempt = 0; attempt < 16u; ++attempt) {
-    const uint4 wt = philox_s(key0, key1, gene, c1, (TAG_COUNT << 16) | chi, 0xffffffffu - attempt);
-    const double hi = attempt == 0 ? (double)w : (double)wt.y;
-    const double u = (hi + ((double)wt.x + 0.5) * 2.3283064365386963e-10) * 2.3283064365386963e-10 * stretch;
-    double p = p0, cdf = p0;
-    bool above = false;
-    k = 0;
-    while (cdf < u) {
-      // past the mode with a term that cannot move the cdf any more: u lies above the top T
-      if (k >= HY_KMAX64 || (p < 1e-18 && (float)k > mu)) { above = true; break; }
-      p *= fma(q, (double)k, a) / (double)(k + 1);             // P(k+1) = P(k) (a + q k)/(k+1)
-      cdf += p;
-      ++k;
-    }
-    if (!above) break;
-  }
-  return k;
-}
-
 __device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
   return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
 }
@@ -228,6 +187,80 @@ __host__ __device__ constexpr RcpTail make_rcp_tail() {
 }
 __constant__ __align__(16) RcpTail c_rcp_tail = make_rcp_tail();
 
+// 1/k!, k = 0..33 (immediates after unrolling; 1/33! = 1.15e-37 is the last normal fp32 value of the series)
+#define PST_INV_FACT_TABLE {1.000000000e+00f, 1.000000000e+00f, 5.000000000e-01f, 1.666666667e-01f,               \
+    4.166666667e-02f, 8.333333333e-03f, 1.388888889e-03f, 1.984126984e-04f, 2.480158730e-05f, 2.755731922e-06f,   \
+    2.755731922e-07f, 2.505210839e-08f, 2.087675699e-09f, 1.605904384e-10f, 1.147074560e-11f, 7.647163732e-13f,   \
+    4.779477332e-14f, 2.811457254e-15f, 1.561920697e-16f, 8.220635247e-18f, 4.110317623e-19f, 1.957294106e-20f,   \
+    8.896791392e-22f, 3.868170171e-23f, 1.611737571e-24f, 6.446950284e-26f, 2.479596263e-27f, 9.183689864e-29f,   \
+    3.279889237e-30f, 1.130996289e-31f, 3.769987629e-33f, 1.216125042e-34f, 3.800390755e-36f, 1.151633562e-37f}
+
+// runtime-indexed copy of 1/k! for the tail path (the kernels use the immediates)
+__constant__ float c_inv_fact[34] = PST_INV_FACT_TABLE;
+
+// one term of the inversion in the head's form: t_{k+1} = t_k (a + q k), t_k = P(k) k!
+__device__ __forceinline__ float inv_t_next(float t, float a, float q, int k) {
+  return t * ((k == 0) ? a : fmaf(q, (float)k, a));
+}
+
+// Far upper tail of the inversion (the top 2^-14 of the uniforms, listed by the draw kernel by the
+// Philox word alone and finished by tail_fix_kernel) and the redraws.  fp32 cannot resolve the cdf next
+// to 1 (spacing 6e-8) and its uniform has 24 bits, so these counts are inverted with a 64-bit uniform -
+// the head's word w refined by 32 more random bits, U = (w + (w2 + 1/2) 2^-32) 2^-32, stretched like
+// the fp32 uniform (u = U (1 + 2^-15)) - against a cdf accumulated in fp64.  The pmf terms are the
+// SAME fp32 numbers the head and the search drain add up (t_k = P(k) k! through k = 33, then P(k)
+// itself; same functions, same tables): the two cdfs differ only by the unbiased rounding of the fp32
+// accumulation, so they join where the route switches.  (An independent fp64 pmf does not: after ~200
+// terms the fp32 terms have drifted by ~5e-7 of cdf, which showed as one displaced bin at 1e9 draws.)
+// The cdf tops out at T = 1 + eps like the head's.  u >= T (probability ~2^-15) has no crossing: the
+// count is redrawn with a fresh 64-bit uniform over the whole range, so that accepted draws follow
+// p(k) / T, the exact pmf up to the relative rounding of its terms.  Random words: blocks 0xffffffff,
+// 0xfffffffe, ... of the count's own (cell, gene) stream, which the mixture (blocks 2a, 2a+1, a <= 62)
+// never reaches.
+constexpr int HY_KMAX64 = 1 << 16;
+__device__ __forceinline__ int invert_tail(float mu, float th, uint32_t key0, uint32_t key1, uint32_t gene,
+                                           int64_t cell) {
+  float q, a, e2;
+  nb_inversion_params(mu, th, q, a, e2);
+  const float p0 = ex2_fast(e2);
+  const uint32_t c1 = (uint32_t)cell, chi = (uint32_t)((uint64_t)cell >> 32);
+  const uint4 wq = philox_s(key0, key1, gene >> 2, c1, (TAG_QUAD << 16) | chi, 0u);   // the head's block
+  const uint32_t j4 = gene & 3u;
+  const uint32_t w = j4 == 0 ? wq.x : j4 == 1 ? wq.y : j4 == 2 ? wq.z : wq.w;
+  const double stretch = 1.0 + (double)kInversionStretch;
+  int k = 0;
+  for (uint32_t attempt = 0; attempt < 16u; ++attempt) {
+    const uint4 wt = philox_s(key0, key1, gene, c1, (TAG_COUNT << 16) | chi, 0xffffffffu - attempt);
+    const double hi = attempt == 0 ? (double)w : (double)wt.y;
+    const double u = (hi + ((double)wt.x + 0.5) * 2.3283064365386963e-10) * 2.3283064365386963e-10 * stretch;
+    float t = p0;
+    double cdf = (double)p0;
+    bool above = false;
+    k = 0;
+    while (cdf < u && k < HY_TAIL0) {                       // head + stage 2 of the drain: t_k form
+      t = inv_t_next(t, a, q, k);
+      cdf += (double)t * (double)c_inv_fact[k + 1];
+      ++k;
+    }
+    if (cdf < u) {                                          // the drain's open-ended loop: P(k) form
+      float pp = t * c_inv_fact[HY_TAIL0];
+      float ak = fmaf(q, (float)HY_TAIL0, a);
+      while (cdf < u) {
+        // past the mode with a term that cannot move the cdf any more: u lies above the top T
+        if (k >= HY_KMAX64 || (pp < 1e-30f && (float)k > mu)) { above = true; break; }
+        const int j = k - HY_TAIL0;
+        const float rk = j < HY_KMAX ? c_rcp_tail.v[j] : 1.0f / (float)(k + 1);
+        pp *= ak * rk;                                      // P(k+1) = P(k) (a + q k)/(k+1)
+        cdf += (double)pp;
+        ak += q;
+        ++k;
+      }
+    }
+    if (!above) break;
+  }
+  return k;
+}
+
 // work-scheduler words of pst_draw_counts: [slot][0] next chunk, [slot][1] warps that have left; one
 // slot per (device, stream), see sched_slot().  Zero between launches (the last warp rearms them).
 __device__ unsigned int g_sched[PST_SCHED_SLOTS][2];
@@ -239,14 +272,6 @@ struct HyWarpQueues {
   int ga[HY_QCAP];          //          attempt counter of the current stage | stage << 16
   float4 mstage[32];        // next cell's means quad, filled by cp.async (one slot per lane)
 };
-
-// 1/k!, k = 0..33 (immediates after unrolling; 1/33! = 1.15e-37 is the last normal fp32 value of the series)
-#define PST_INV_FACT_TABLE {1.000000000e+00f, 1.000000000e+00f, 5.000000000e-01f, 1.666666667e-01f,               \
-    4.166666667e-02f, 8.333333333e-03f, 1.388888889e-03f, 1.984126984e-04f, 2.480158730e-05f, 2.755731922e-06f,   \
-    2.755731922e-07f, 2.505210839e-08f, 2.087675699e-09f, 1.605904384e-10f, 1.147074560e-11f, 7.647163732e-13f,   \
-    4.779477332e-14f, 2.811457254e-15f, 1.561920697e-16f, 8.220635247e-18f, 4.110317623e-19f, 1.957294106e-20f,   \
-    8.896791392e-22f, 3.868170171e-23f, 1.611737571e-24f, 6.446950284e-26f, 2.479596263e-27f, 9.183689864e-29f,   \
-    3.279889237e-30f, 1.130996289e-31f, 3.769987629e-33f, 1.216125042e-34f, 3.800390755e-36f, 1.151633562e-37f}
 
 #ifndef HY_MIN_CTAS
 #define HY_MIN_CTAS 7     // 28 warps/SM: up to 72 registers (69 used) and 29.5 KB of queues per CTA
@@ -293,7 +318,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 #pragma unroll
     for (int s2 = 0; s2 < HY_STAGE2; ++s2) {
       const int k = KFIX - 1 + s2;
-      tt *= fmaf(qq, (float)k, aa);                          // t_{k+1}
+      tt = inv_t_next(tt, aa, qq, k);                        // t_{k+1}
       dd = fmaf(tt, inv_fact[k + 1], dd);                    // cdf(k+1) - u
       cn += (int)(__float_as_uint(dd) >> 31);
     }
@@ -392,6 +417,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     // lanes past the last quad of the last strip repeat quad Q-1: same key, same counts, same
     // addresses, so the duplicates are harmless and no per-count "lane is live" predicate is needed
     const uint32_t quad = min(strip * 32u + (uint32_t)lane, Q - 1u);
+    const bool lane_first = strip * 32u + (uint32_t)lane < Q;     // not one of the repeated edge lanes
     const uint32_t g0 = quad * 4u;
     const int64_t cell_lo = (int64_t)cgroup * HY_CHUNK_CELLS;
     const int n_cells = (int)((n - cell_lo) < HY_CHUNK_CELLS ? (n - cell_lo) : HY_CHUNK_CELLS);
@@ -496,12 +522,14 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (small[j] && (fw[j] >= kTailWord) && (VEC || g0 + j < G)) {
-            const unsigned slot = atomicAdd(tail, 1u);
-            if (slot < tail_cap)
-              reinterpret_cast<uint4 *>(tail + 4)[slot] =
-                  make_uint4((uint32_t)cell, g0 + j, __float_as_uint(mu[j]), __float_as_uint(th[j]));
-            else
-              flag |= PST_FLAG_SCRATCH;
+            if (lane_first) {                          // repeated edge lanes leave the listing to their twin
+              const unsigned slot = atomicAdd(tail, 1u);
+              if (slot < tail_cap)
+                reinterpret_cast<uint4 *>(tail + 4)[slot] =
+                    make_uint4((uint32_t)cell, g0 + j, __float_as_uint(mu[j]), __float_as_uint(th[j]));
+              else
+                flag |= PST_FLAG_SCRATCH;
+            }
             fw[j] = -4.0e9f;
           }
         }
@@ -535,7 +563,7 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
       for (int k = 0; k < KFIX - 1; ++k) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          t[j] *= (k == 0) ? a[j] : fmaf(q[j], (float)k, a[j]);  // t_{k+1} = P(k+1) (k+1)!
+          t[j] = inv_t_next(t[j], a[j], q[j], k);                // t_{k+1} = P(k+1) (k+1)!
           d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
           cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
         }
@@ -622,7 +650,7 @@ __global__ void tail_fix_kernel(const __grid_constant__ PhiloxKey key, const uin
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint4 e = reinterpret_cast<const uint4 *>(tail + 4)[i];
     X[(uint64_t)e.x * ldx + e.y] =
-        invert_tail_f64(__uint_as_float(e.z), __uint_as_float(e.w), key.k0[0], key.k1[0], e.y, cell0 + (int64_t)e.x);
+        invert_tail(__uint_as_float(e.z), __uint_as_float(e.w), key.k0[0], key.k1[0], e.y, cell0 + (int64_t)e.x);
   }
 }
 

@@ -144,6 +144,14 @@ narrow_kernel(const int32_t *__restrict__ X, int64_t n, int64_t G, int64_t ldx, 
   }
 }
 
+// Pure-store kernel: the write-only HBM ceiling the count write is measured against.  Same
+// shape of traffic as the sampler's output: 128-bit stores, 512 contiguous bytes per warp instruction.
+__global__ void __launch_bounds__(256) store_fill_kernel(int4 *__restrict__ out, int64_t n16, int32_t value) {
+  const int4 v = make_int4(value, value, value, value);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) out[i] = v;
+}
+
 inline unsigned stream_grid(int64_t threads) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, (int64_t)num_sm() * 16));
 }
@@ -177,6 +185,16 @@ extern "C" int pst_transform_counts(const int32_t *X, int64_t n, int64_t G, int6
   else if (mode == PST_TRANSFORM_NORMALIZE_LOG1P) PST_LAUNCH_TRANSFORM(PST_TRANSFORM_NORMALIZE_LOG1P);
   else PST_LAUNCH_TRANSFORM(PST_TRANSFORM_LOG1P);
 #undef PST_LAUNCH_TRANSFORM
+  return check_launch(fn);
+}
+
+extern "C" int pst_store_fill(int32_t *out, int64_t n, int32_t value, void *stream) {
+  const char *fn = "pst_store_fill";
+  PST_REQUIRE(n >= 0 && n % 4 == 0, fn, "n must be a non-negative multiple of 4");
+  if (n == 0) return 0;
+  PST_REQUIRE(out && (uintptr_t)out % 16 == 0, fn, "out must be a 16-byte aligned device pointer");
+  store_fill_kernel<<<(unsigned)((int64_t)num_sm() * 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<int4 *>(out), n / 4, value);
   return check_launch(fn);
 }
 

@@ -1,0 +1,110 @@
+// Host side of the device -> host path: the count matrix crosses PCIe in a narrow format
+// (uint8 / uint16 with an exact overflow list, or int32) into pinned staging buffers, and these
+// multi-threaded routines expand it into the caller's matrix (int32, or the reference's int64:
+// prosstt/simulation.py:651 returns the int64 array of scipy's nbinom.rvs) while the GPU samples
+// the next chunk.  Pure data movement: no sampling arithmetic runs on the CPU.
+//
+// Plain C ABI (include/prosstt_b200.h): host pointers, sizes, a thread count.
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include <vector>
+#include "../../include/prosstt_b200.h"
+
+namespace {
+
+int clamp_threads(int threads, int64_t n, int64_t min_per_thread) {
+  int hw = (int)std::thread::hardware_concurrency();
+  if (hw <= 0) hw = 1;
+  if (threads <= 0) threads = hw;
+  const int64_t useful = std::max<int64_t>(1, n / std::max<int64_t>(1, min_per_thread));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 256), useful));
+}
+
+// run fn(lo, hi) over [0, n) cut into `threads` contiguous slices aligned to 64 elements
+template <class F>
+void parallel_slices(int64_t n, int threads, F fn) {
+  if (threads <= 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> pool;
+  pool.reserve(threads - 1);
+  const int64_t per = ((n + threads - 1) / threads + 63) & ~(int64_t)63;
+  for (int t = 1; t < threads; ++t) {
+    const int64_t lo = std::min(n, per * t), hi = std::min(n, per * (t + 1));
+    if (lo < hi) pool.emplace_back([=] { fn(lo, hi); });
+  }
+  fn((int64_t)0, std::min(n, per));
+  for (auto &th : pool) th.join();
+}
+
+template <class S, class D>
+__attribute__((target_clones("avx512f", "avx2", "default")))
+void widen_slice(const S *__restrict__ src, D *__restrict__ dst, int64_t lo, int64_t hi) {
+  for (int64_t i = lo; i < hi; ++i) dst[i] = (D)src[i];
+}
+
+template <class S, class D>
+void widen(const void *src, void *dst, int64_t n, int threads) {
+  const S *s = static_cast<const S *>(src);
+  D *d = static_cast<D *>(dst);
+  parallel_slices(n, clamp_threads(threads, n, 1 << 16), [=](int64_t lo, int64_t hi) { widen_slice<S, D>(s, d, lo, hi); });
+}
+
+__attribute__((target_clones("avx512f", "avx2", "default")))
+uint64_t sum_words(const uint32_t *__restrict__ p, int64_t lo, int64_t hi) {
+  uint64_t a = 0;
+  for (int64_t i = lo; i < hi; ++i) a += p[i];
+  return a;
+}
+
+}  // namespace
+
+extern "C" int pst_host_widen(const void *src, int32_t src_bits, void *dst, int32_t dst_bits, int64_t n,
+                              int32_t threads) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return -1;
+  if (n == 0) return 0;
+  if (src_bits == 8 && dst_bits == 32) widen<uint8_t, int32_t>(src, dst, n, threads);
+  else if (src_bits == 16 && dst_bits == 32) widen<uint16_t, int32_t>(src, dst, n, threads);
+  else if (src_bits == 8 && dst_bits == 64) widen<uint8_t, int64_t>(src, dst, n, threads);
+  else if (src_bits == 16 && dst_bits == 64) widen<uint16_t, int64_t>(src, dst, n, threads);
+  else if (src_bits == 32 && dst_bits == 64) widen<int32_t, int64_t>(src, dst, n, threads);
+  else if (src_bits == 32 && dst_bits == 32) {
+    const char *s = static_cast<const char *>(src);
+    char *d = static_cast<char *>(dst);
+    parallel_slices(n, clamp_threads(threads, n, 1 << 16),
+                    [=](int64_t lo, int64_t hi) { memcpy(d + 4 * lo, s + 4 * lo, (size_t)(4 * (hi - lo))); });
+  } else {
+    return -1;
+  }
+  return 0;
+}
+
+// dst[index[i] - base] = value[i] for the entries with base <= index[i] < base + n (the exact values of
+// the elements that saturated the narrow format); dst holds dst_bits-wide integers.
+extern "C" int pst_host_apply_overflow(void *dst, int32_t dst_bits, int64_t base, int64_t n, const int64_t *index,
+                                       const int32_t *value, int64_t entries) {
+  if (entries < 0 || n < 0 || (entries > 0 && (!dst || !index || !value))) return -1;
+  if (dst_bits != 32 && dst_bits != 64) return -1;
+  for (int64_t i = 0; i < entries; ++i) {
+    const int64_t at = index[i] - base;
+    if (at < 0 || at >= n) continue;
+    if (dst_bits == 32) static_cast<int32_t *>(dst)[at] = value[i];
+    else static_cast<int64_t *>(dst)[at] = (int64_t)value[i];
+  }
+  return 0;
+}
+
+// Sum of the buffer read as uint32 words (bytes must be a multiple of 4): the cheapest sink that
+// still touches every byte; used by the streamed C5 benchmark and as a transfer checksum.
+extern "C" uint64_t pst_host_checksum(const void *src, int64_t bytes, int32_t threads) {
+  if (!src || bytes <= 0) return 0;
+  const int64_t n = bytes / 4;
+  const uint32_t *p = static_cast<const uint32_t *>(src);
+  const int t = clamp_threads(threads, n, 1 << 18);
+  std::vector<uint64_t> part((size_t)t + 1, 0);
+  const int64_t per = ((n + t - 1) / t + 63) & ~(int64_t)63;
+  parallel_slices(n, t, [&](int64_t lo, int64_t hi) { part[(size_t)(lo / per)] = sum_words(p, lo, hi); });
+  uint64_t total = 0;
+  for (uint64_t v : part) total += v;
+  return total;
+}

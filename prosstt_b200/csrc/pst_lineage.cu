@@ -187,6 +187,49 @@ __global__ void pearson_kernel(const double *__restrict__ A, const double *__res
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(out_count, __popc(m));
 }
 
+// ---------------------------------------------------------------------------
+// Acceptance tests of simulate_lineage for a whole batch of candidate branches in ONE launch
+// (simulation.py:270-272): item i < n_slots -> maximum of the candidate's (T x G) rel rows (cutoff
+// test); item n_slots + p -> number of genes with Pearson r < 0 between two row blocks (sibling
+// divergence, same arithmetic as pearson_kernel).  blockIdx.y = item, blockIdx.x = 128-gene block.
+// ---------------------------------------------------------------------------
+__global__ void lineage_checks_kernel(const double *__restrict__ rel, int64_t G, int n_slots,
+                                      const int64_t *__restrict__ slot_row, const int32_t *__restrict__ slot_T,
+                                      const int64_t *__restrict__ pair_a, const int64_t *__restrict__ pair_b,
+                                      const int32_t *__restrict__ pair_n, double *__restrict__ slot_max,
+                                      int32_t *__restrict__ pair_neg) {
+  const int item = blockIdx.y;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < n_slots) {
+    const double *A = rel + slot_row[item] * G;
+    const int64_t n = slot_T[item];
+    double m = -INFINITY;
+    if (g < G)
+      for (int64_t t = 0; t < n; ++t) m = fmax(m, A[t * G + g]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomic_max_f64(slot_max + item, m);
+    return;
+  }
+  const int p = item - n_slots;
+  const double *A = rel + pair_a[p] * G, *B = rel + pair_b[p] * G;
+  const int64_t n = pair_n[p];
+  int neg = 0;
+  if (g < G) {
+    double sa = 0, sb = 0;
+    for (int64_t t = 0; t < n; ++t) { sa += A[t * G + g]; sb += B[t * G + g]; }
+    const double ma = sa / (double)n, mb = sb / (double)n;
+    double sab = 0, saa = 0, sbb = 0;
+    for (int64_t t = 0; t < n; ++t) {
+      const double a = A[t * G + g] - ma, b = B[t * G + g] - mb;
+      sab = fma(a, b, sab); saa = fma(a, a, saa); sbb = fma(b, b, sbb);
+    }
+    neg = (saa > 0.0 && sbb > 0.0 && sab < 0.0) ? 1 : 0;   // NaN r (constant column) is not < 0
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, neg);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(pair_neg + p, __popc(m));
+}
+
 __global__ void f64_to_f32_kernel(const double *__restrict__ in, int64_t n, double min_positive,
                                   float *__restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -273,6 +316,23 @@ extern "C" int pst_pearson_anticorr(const double *A, const double *B, int64_t nr
   if (G == 0) return 0;
   PST_REQUIRE(A && B && out_count, fn, "null pointer");
   pearson_kernel<<<(unsigned)((G + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, B, nrows, G, out_count);
+  return check_launch(fn);
+}
+
+extern "C" int pst_lineage_checks(const double *rel, int64_t G, int32_t n_slots, const int64_t *slot_row,
+                                  const int32_t *slot_T, int32_t n_pairs, const int64_t *pair_a,
+                                  const int64_t *pair_b, const int32_t *pair_n, double *out_slot_max,
+                                  int32_t *out_pair_neg, void *stream) {
+  const char *fn = "pst_lineage_checks";
+  PST_REQUIRE(G >= 0 && n_slots >= 0 && n_pairs >= 0, fn, "negative size");
+  PST_REQUIRE((int64_t)n_slots + n_pairs <= 65535, fn, "at most 65535 candidates + pairs per call");
+  if (G == 0 || n_slots + n_pairs == 0) return 0;
+  PST_REQUIRE(rel, fn, "null pointer");
+  PST_REQUIRE(n_slots == 0 || (slot_row && slot_T && out_slot_max), fn, "null pointer (candidates)");
+  PST_REQUIRE(n_pairs == 0 || (pair_a && pair_b && pair_n && out_pair_neg), fn, "null pointer (pairs)");
+  const dim3 grid((unsigned)((G + 127) / 128), (unsigned)(n_slots + n_pairs));
+  lineage_checks_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rel, G, n_slots, slot_row, slot_T, pair_a, pair_b,
+                                                                pair_n, out_slot_max, out_pair_neg);
   return check_launch(fn);
 }
 

@@ -117,16 +117,33 @@ def choice_cdf(p):
     return cdf
 
 
+def _content_key(m):
+    """Cheap fingerprint of one branch's means for the device-table cache: buffer address, shape and
+    every 17th value (a stride coprime to any G that is not a multiple of 17 visits every row and every
+    gene column).  An in-place edit of a row, a column or the whole array of tree.means[b] - ordinary
+    NumPy usage in scripts written for the reference - changes it, unlike id(); after editing single
+    elements call tree.invalidate_device_cache()."""
+    if isinstance(m, torch.Tensor):
+        return ("t", m.data_ptr(), tuple(m.shape), m._version)
+    a = np.asarray(m)
+    flat = a.reshape(-1)
+    step = 17 if (a.ndim < 2 or a.shape[-1] % 17) else 19
+    return (a.__array_interface__["data"][0], a.shape, flat[::step].tobytes())
+
+
 def means_table(tree, tables, dev):
     """(P, G) fp32 means table in HBM, built once per tree.means and cached on the tree."""
     if tree.means is None:
         raise ValueError("the tree has no mean expression yet: call add_genes() or "
                          "default_gene_expression() first")
     if hasattr(tree.means, "table32"):                 # simulation.DeviceMeans: already in HBM
-        if tree.means.table32.device == dev and tuple(tree.means.table32.shape) == (tables.P, int(tree.G)):
+        if tuple(tree.means.table32.shape) != (tables.P, int(tree.G)):
+            raise ValueError("the device-resident means table has shape %s, the tree needs %s"
+                             % (tuple(tree.means.table32.shape), (tables.P, int(tree.G))))
+        if tree.means.table32.device == dev:
             return tree.means.table32
         return tree.means.table32.to(dev)
-    key = ("means32", str(dev), id(tree.means)) + tuple(id(tree.means[b]) for b in tables.names)
+    key = ("means32", str(dev)) + tuple(_content_key(tree.means[b]) for b in tables.names)
     cache = tree.__dict__.setdefault("_device_cache", {})
     hit = cache.get(key)
     if hit is not None:
@@ -176,8 +193,28 @@ def raise_flags(word):
         raise OverflowError("a sampled count exceeded the int32 range")
 
 
+_NP_TO_TORCH = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+                np.dtype(np.uint16): torch.uint16, np.dtype(np.uint8): torch.uint8}
+_STAGE_BYTES = 256 << 20                      # one pinned staging buffer (two per device)
+_STAGING = {}
+
+
+def _pinned_staging(dev, nbytes):
+    """Two pinned host buffers of at least nbytes for the staged device->host path, allocated once per
+    device and kept (page-locking costs ~0.2 s per GB)."""
+    key = str(dev)
+    have = _STAGING.get(key)
+    if have is None or have[0].numel() < nbytes:
+        size = max(int(nbytes), 1)
+        have = [torch.empty(size, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        _STAGING[key] = have
+    return have
+
+
 class CountEngine(object):
     """draw_counts on one GPU: replicated small state + a cell range to sample."""
+
+    timers = None     # set to a list to collect (start, end) CUDA events around every draw (bench.py)
 
     def __init__(self, tree, tables, alpha, beta, dev, sampler="gamma_poisson"):
         self.dev = dev
@@ -199,6 +236,10 @@ class CountEngine(object):
             out = torch.empty((n, self.G), dtype=torch.int32, device=self.dev)
         st = nat.stream_ptr(self.dev)
         order = None
+        timers = CountEngine.timers
+        if timers is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(torch.cuda.current_stream(self.dev))
         if self.group_rows and n >= 2048 and self.sampler == nat.SAMPLER_HYBRID:
             # visit the cells grouped by tree row: concurrently running warps then share means rows
             if self._order is None or self._order.numel() < n:
@@ -218,22 +259,149 @@ class CountEngine(object):
                  nat.ptr(scaling32), nat.ptr(self.alpha), nat.ptr(self.beta_m1),
                  seed, int(cell0), n, out.data_ptr(), out.stride(0) if n else self.G,
                  nat.ptr(self.flags), self.sampler, order, scratch, words, st)
+        if timers is not None:
+            t1 = torch.cuda.Event(enable_timing=True)
+            t1.record(torch.cuda.current_stream(self.dev))
+            timers.append((t0, t1))
         return out
 
-    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=None):
-        """Sample in cell chunks and stream them into `host_out` (an (n, G) CPU tensor, ideally
-        pinned): sampling of chunk i+1 overlaps the copy of chunk i.
+    def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=None,
+                     transport=None, threads=0):
+        """Sample in cell chunks and stream them into `host_out`, an (n, G) CPU tensor or C-contiguous
+        NumPy array: sampling of chunk i+1 overlaps the transfer (and host-side expansion) of chunk i.
 
-        host_out.dtype int32: the counts as sampled (4 B per count over PCIe).
-        host_out.dtype uint16 / uint8: the narrow transfer formats (2 / 1 B per count):
-        min(count, SAT) with SAT = 65535 / 255, and every element that reads SAT is listed exactly
-        in `self.overflow` = (flat index into host_out, int32 value) NumPy arrays sorted by index
-        (formats.widen rebuilds int32).  At default depth about 2 in 10^4 counts reach 255 and none
-        reaches 65535."""
+        host_out int32, pinned, transport None/"direct": the counts as sampled are copied straight into
+          it (4 B per count over PCIe).
+        host_out uint16 / uint8 (pinned): the narrow formats themselves (2 / 1 B per count):
+          min(count, SAT) with SAT = 65535 / 255, and every element that reads SAT is listed exactly in
+          `self.overflow` = (flat index into host_out, int32 value) NumPy arrays sorted by index
+          (formats.widen rebuilds int32).  At default depth about 2 in 10^4 counts reach 255 and none
+          reaches 65535.
+        host_out int32 or int64, pageable or pinned, transport "u8" / "u16" / "i32": the chunk crosses
+          PCIe in the transport format into pinned staging buffers (cached per device) and host threads
+          (pst_host_widen) expand it into host_out, the overflow list is applied at the end: the caller
+          receives exact int32 / int64 counts.  This is the path of the reference-shaped call, which
+          returns a fresh (pageable) int64 array.  Default transport: "i32" for pageable targets."""
+        n = int(rows.numel())
+        is_np = isinstance(host_out, np.ndarray)
+        if is_np:
+            if not host_out.flags.c_contiguous or not host_out.flags.writeable:
+                raise ValueError("host_out must be a writeable C-contiguous array")
+            hdt = _NP_TO_TORCH.get(host_out.dtype)
+            pinned = False
+        else:
+            hdt = host_out.dtype
+            pinned = host_out.is_pinned() and host_out.is_contiguous()
+        if hdt not in (torch.int32, torch.int64, torch.uint16, torch.uint8) or tuple(host_out.shape) != (n, self.G):
+            raise ValueError("host_out must be an int32, int64, uint16 or uint8 CPU matrix of shape (%d, %d)"
+                             % (n, self.G))
+        narrow_dst = hdt in (torch.uint16, torch.uint8)
+        if transport in (None, "direct") and not is_np and hdt != torch.int64 and \
+                (pinned or narrow_dst or transport == "direct"):
+            return self._draw_to_host_direct(rows, scaling32, seed, cell0, host_out, chunk_cells, overflow_cap)
+        if narrow_dst:
+            raise ValueError("a uint16 / uint8 host matrix must be a CPU tensor and takes transport 'direct'")
+        return self._draw_to_host_staged(rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
+                                         transport or "i32", threads)
+
+    def stream_chunks(self, rows, scaling32, seed, cell0, consume, transport="i32", chunk_cells=None,
+                      overflow_cap=None):
+        """Sample in cell chunks, move each chunk over PCIe in the transport format ("i32", "u16", "u8")
+        into one of two pinned staging buffers and hand it to `consume(staged, lo, hi)` on a worker
+        thread (`staged`: pinned uint8 tensor holding rows [lo, hi) in the transport format) while the
+        next chunk is sampled and copied.  The matrix is never resident anywhere: this is the streamed
+        path for outputs larger than HBM (config 5: 600 GB).  Returns the overflow list of the narrow
+        transports as CPU tensors (flat index, exact value), unsorted, or None."""
+        import concurrent.futures
+        n, G = int(rows.numel()), self.G
+        tdt = {"u8": torch.uint8, "u16": torch.uint16, "i32": torch.int32}.get(transport)
+        if tdt is None:
+            raise ValueError("transport must be 'i32', 'u16' or 'u8'")
+        width = torch.empty(0, dtype=tdt).element_size()
+        narrow = width < 4
+        if chunk_cells is None:
+            chunk_cells = max(1, min(n, _STAGE_BYTES // max(1, width * G)))
+        if narrow and overflow_cap is None:
+            overflow_cap = (1 << 20) if width == 2 else max(1 << 20, n * G // 100)
+        dev = self.dev
+        stage_dev = [torch.empty((chunk_cells, G), dtype=tdt, device=dev) for _ in range(2)]
+        stage_host = _pinned_staging(dev, chunk_cells * G * width)
+        if narrow:
+            work = torch.empty((chunk_cells, G), dtype=torch.int32, device=dev)
+            ovf_index = torch.empty(max(1, overflow_cap), dtype=torch.int64, device=dev)
+            ovf_value = torch.empty(max(1, overflow_cap), dtype=torch.int32, device=dev)
+            ovf_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        pending = [None, None]                      # consumer still reading stage_host[k]
+
+        def landed(k, lo, hi, event):
+            event.synchronize()                     # the chunk is in stage_host[k]
+            consume(stage_host[k][:(hi - lo) * G * width], lo, hi)
+
+        try:
+            for i, lo in enumerate(range(0, n, chunk_cells)):
+                hi, k = min(n, lo + chunk_cells), i & 1
+                if pending[k] is not None:
+                    pending[k].result()             # stage_host[k] (and so stage_dev[k]) is free again
+                buf = stage_dev[k][:hi - lo]
+                if narrow:
+                    self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=work[:hi - lo])
+                    nat.call("pst_narrow_counts", work.data_ptr(), hi - lo, G, G, buf.data_ptr(), G, 8 * width, lo,
+                             ovf_index, ovf_value, int(overflow_cap), ovf_count, nat.stream_ptr(dev))
+                else:
+                    self.draw(rows[lo:hi], scaling32[lo:hi], seed, cell0 + lo, out=buf)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    stage_host[k][:(hi - lo) * G * width].copy_(buf.view(torch.uint8).view(-1), non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(copy_stream)
+                pending[k] = pool.submit(landed, k, lo, hi, copied)
+            for f in pending:
+                if f is not None:
+                    f.result()
+        finally:
+            pool.shutdown(wait=True)
+        if not narrow:
+            return None
+        count = int(ovf_count.item())
+        if count > overflow_cap:
+            raise OverflowError("%d counts reach the saturation value of the %s transport but the overflow "
+                                "list holds %d: use a wider transport or a larger overflow_cap"
+                                % (count, transport, overflow_cap))
+        return ovf_index[:count].cpu(), ovf_value[:count].cpu()
+
+    def _draw_to_host_staged(self, rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
+                             transport, threads):
+        n, G = int(rows.numel()), self.G
+        width = {"u8": 1, "u16": 2, "i32": 4}.get(transport)
+        if width is None:
+            raise ValueError("transport must be 'direct', 'i32', 'u16' or 'u8'")
+        dst_bits = 32 if hdt == torch.int32 else 64
+        dst_ptr = host_out.ctypes.data if isinstance(host_out, np.ndarray) else host_out.data_ptr()
+        lib = nat.load()
+        self.overflow = None
+
+        def expand(staged, lo, hi):
+            rc = lib.pst_host_widen(staged.data_ptr(), 8 * width, dst_ptr + lo * G * (dst_bits // 8), dst_bits,
+                                    (hi - lo) * G, int(threads))
+            if rc != 0:
+                raise nat.NativeError("pst_host_widen failed")
+
+        listed = self.stream_chunks(rows, scaling32, seed, cell0, expand, transport, chunk_cells, overflow_cap)
+        if listed is not None:
+            index, value = listed
+            lib.pst_host_apply_overflow(dst_ptr, dst_bits, 0, n * G, index.data_ptr(), value.data_ptr(),
+                                        int(index.numel()))
+        return host_out
+
+    def _draw_to_host_direct(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=None):
+        """Chunks copied straight into a pinned CPU tensor of the transfer dtype (see draw_to_host)."""
         n = int(rows.numel())
         narrow = host_out.dtype in (torch.uint16, torch.uint8)
-        if not narrow and host_out.dtype != torch.int32:
-            raise ValueError("host_out must be an int32, uint16 or uint8 CPU tensor")
         width = host_out.element_size()
         if narrow and overflow_cap is None:
             # uint8 lists every count >= 255 (2e-4 of them at default depth; allow 50x that)

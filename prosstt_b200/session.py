@@ -23,6 +23,7 @@ class DensitySession(object):
         self.dev = nat.device(device)
         self.tree = tree
         self.n, self.first = int(cells), int(first)
+        self.capacity = self.n
         self.scale, self.scale_mean, self.scale_v = scale, float(scale_mean), float(scale_v)
         self.tables = TreeTables(tree, self.dev)
         self.engine = CountEngine(tree, self.tables, alpha, beta, self.dev, sampler=sampler)
@@ -39,6 +40,14 @@ class DensitySession(object):
         self.s32 = torch.empty(n, dtype=torch.float32, device=dev)
         self.X = torch.empty((n, self.G), dtype=torch.int32, device=dev) if resident_output else None
         self.t_draw = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+
+    def set_range(self, first, cells=None):
+        """Re-target the session at the global cell range [first, first + cells), cells <= the size it
+        was built with: a long run is sampled chunk after chunk through one set of buffers."""
+        n = self.capacity if cells is None else int(cells)
+        if not 0 <= n <= self.capacity:
+            raise ValueError("a session built for %d cells cannot sample %d" % (self.capacity, n))
+        self.n, self.first = n, int(first)
 
     # -- per-call host inputs of sample_density(tree, N, alpha, beta): density + gene params
     def upload_inputs(self):
@@ -70,10 +79,11 @@ class DensitySession(object):
     def step(self, seed):
         """One sample_density pass into the resident slab.  Stream-ordered, no sync."""
         self.index_and_scalings(seed)
+        n = self.n
         self.t_draw[0].record()
-        self.engine.draw(self.rows, self.s32, nat.derive_seed(seed, 2), self.first, out=self.X)
+        self.engine.draw(self.rows[:n], self.s32[:n], nat.derive_seed(seed, 2), self.first, out=self.X[:n])
         self.t_draw[1].record()
-        return self.X
+        return self.X[:n]
 
     def last_draw_ms(self):
         """Device time of the last draw kernel (call after a synchronize)."""
@@ -85,12 +95,13 @@ class DensitySession(object):
         bytes copied device->host.  Synchronises before returning.  host_X may be int32, uint16 or
         uint8 (narrow transfer formats; the saturated elements are then in `self.engine.overflow`)."""
         self.index_and_scalings(seed)
-        self.engine.draw_to_host(self.rows, self.s32, nat.derive_seed(seed, 2), self.first, host_X,
+        n = self.n
+        self.engine.draw_to_host(self.rows[:n], self.s32[:n], nat.derive_seed(seed, 2), self.first, host_X,
                                  chunk_cells=chunk_cells)
         nbytes = host_X.numel() * host_X.element_size()
         for src, dst in ((self.pt, host_pt), (self.codes, host_codes), (self.s64, host_scal)):
             if dst is not None:
-                dst.copy_(src, non_blocking=True)
+                dst.copy_(src[:n], non_blocking=True)
                 nbytes += dst.numel() * dst.element_size()
         torch.cuda.current_stream(self.dev).synchronize()
         self.engine.check()
@@ -99,5 +110,6 @@ class DensitySession(object):
     def results(self):
         """(X, pseudotime, branches, scalings) of the last step as numpy (reference types)."""
         self.engine.check()
-        return (self.X.cpu().numpy(), self.pt.cpu().numpy(),
-                self.tables.branch_names(self.codes.cpu().numpy()), self.s64.cpu().numpy())
+        n = self.n
+        return (self.X[:n].cpu().numpy(), self.pt[:n].cpu().numpy(),
+                self.tables.branch_names(self.codes[:n].cpu().numpy()), self.s64[:n].cpu().numpy())

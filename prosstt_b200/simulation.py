@@ -19,6 +19,7 @@ Extra keyword-only arguments (never required):
            chunks: the zero-allocation path for repeated or very large calls
 """
 import warnings
+from collections.abc import Mapping
 
 import numpy as np
 import pandas as pd
@@ -110,16 +111,23 @@ def simulate_coefficients(tree, fallback_a=0.04, **kwargs):
 
 
 class _LineageState(object):
-    """Device buffers of simulate_lineage: packed W (P,K) and rel (P,G) in fp64."""
+    """Device buffers of simulate_lineage: packed W (P,K) and rel (P,G) in fp64, followed by scratch
+    rows that hold the candidate branches of the level being simulated."""
+
+    SCRATCH_BYTES = 8 << 30                      # rel rows of the candidates of one round
 
     def __init__(self, tree, H, dev):
         self.dev = dev
         self.tables = TreeTables(tree, dev)
         self.K, self.G = int(tree.modules), int(tree.G)
         self.H = nat.to_dev(H, torch.float64, dev)
-        P = self.tables.P
-        self.W = torch.zeros((P, max(1, self.K)), dtype=torch.float64, device=dev)
-        self.rel = torch.empty((P, self.G), dtype=torch.float64, device=dev)
+        self.P = P = self.tables.P
+        Tmax = int(self.tables.T.max())
+        # room for at least one candidate of the longest branch, at most SCRATCH_BYTES of rel rows
+        self.S = max(Tmax, min(4 * P, self.SCRATCH_BYTES // max(1, 8 * self.G)))
+        self.Wall = torch.zeros((P + self.S, max(1, self.K)), dtype=torch.float64, device=dev)
+        self.relall = torch.empty((P + self.S, self.G), dtype=torch.float64, device=dev)
+        self.W, self.rel = self.Wall[:P], self.relall[:P]
         self.colmax = torch.empty(self.G, dtype=torch.float64, device=dev)
         top = tree.topology
         self.parent = {}
@@ -131,24 +139,74 @@ class _LineageState(object):
         lo = int(self.tables.row_base[i])
         return lo, lo + int(self.tables.T[i])
 
-    def place_branch(self, b, raw):
-        """Copy a raw (T,K) walk in, carry the parent's end point, form rel rows and the
-        maximum relative expression of the branch.  Returns that maximum (host float)."""
-        st = nat.stream_ptr(self.dev)
-        lo, hi = self.rows(b)
-        K, G = self.K, self.G
-        if K > 0:
-            self.W[lo:hi].copy_(raw)
-            p = self.parent.get(b)
-            if p is not None:
-                plo, phi = self.rows(p)
-                order = torch.tensor([lo, hi - lo, phi - 1], dtype=torch.int32, device=self.dev)
-                nat.call("pst_walk_carry", 1, K, order[0:1].data_ptr(), order[1:2].data_ptr(),
-                         order[2:3].data_ptr(), nat.ptr(self.W), st)
+    def gene_maxima(self):
+        """Per-gene maximum of rel over the whole tree (sim_utils.py:406-426 before the exp), recomputed
+        from W and H without reading the (P, G) table back."""
         self.colmax.fill_(float("-inf"))
-        nat.call("pst_rel_means", nat.ptr(self.W), nat.ptr(self.H), None, lo, hi - lo, K, G,
-                 nat.ptr(self.rel), None, None, nat.ptr(self.colmax), st)
-        return float(self.colmax.max().item())
+        nat.call("pst_rel_means", nat.ptr(self.Wall), nat.ptr(self.H), None, 0, self.P, self.K, self.G,
+                 None, None, None, nat.ptr(self.colmax), nat.stream_ptr(self.dev))
+        return self.colmax
+
+    def try_candidates(self, seed, cands):
+        """One batched round of the rejection loop.  cands = [(branch, attempt), ...] in visiting order.
+        Draws, scans, carries and multiplies every candidate into the scratch rows with one launch per
+        stage.  Returns the scratch row of each candidate."""
+        dev, K, G, P = self.dev, self.K, self.G, self.P
+        st = nat.stream_ptr(dev)
+        tb = self.tables
+        ids = np.array([tb.index[b] for b, _ in cands], dtype=np.int32)
+        att = np.array([a for _, a in cands], dtype=np.int32)
+        T = tb.T[ids].astype(np.int32)
+        row = np.zeros(len(cands), dtype=np.int64)
+        row[1:] = np.cumsum(T.astype(np.int64))[:-1]
+        row += P
+        if K > 0:
+            eps_off = np.zeros(len(cands) + 1, dtype=np.int64)
+            eps_off[1:] = np.cumsum((T.astype(np.int64) - 1) * K)
+            d_T = nat.to_dev(T, torch.int32, dev)
+            d_off = nat.to_dev(eps_off, torch.int64, dev)
+            d_row = nat.to_dev(row.astype(np.int32), torch.int32, dev)
+            n = len(cands) * K
+            u0 = torch.empty(n, dtype=torch.float64, device=dev)
+            v0, eta = torch.empty_like(u0), torch.empty_like(u0)
+            eps = torch.empty(max(1, int(eps_off[-1])), dtype=torch.float64, device=dev)
+            nat.call("pst_walk_draws", seed, len(cands), K, int(T.max()), nat.to_dev(ids, torch.int32, dev),
+                     nat.to_dev(att, torch.int32, dev), d_T, d_off, u0, v0, eta, eps, st)
+            nat.call("pst_walk_scan", len(cands), K, d_row, d_T, d_off, u0, v0, eta, eps, self.Wall, st)
+            plast = np.array([self.rows(self.parent[b])[1] - 1 if b in self.parent else -1 for b, _ in cands],
+                             dtype=np.int32)
+            if np.any(plast >= 0):
+                nat.call("pst_walk_carry", len(cands), K, d_row, d_T, nat.to_dev(plast, torch.int32, dev),
+                         self.Wall, st)
+        nrows = int(T.sum())
+        nat.call("pst_rel_means", nat.ptr(self.Wall), nat.ptr(self.H), None, P, nrows, K, G,
+                 nat.ptr(self.relall), None, None, None, st)
+        return row, T
+
+    def accept(self, b, row):
+        lo, hi = self.rows(b)
+        self.Wall[lo:hi].copy_(self.Wall[row:row + hi - lo])
+        self.relall[lo:hi].copy_(self.relall[row:row + hi - lo])
+
+
+def _bfs_levels(tree):
+    """Branches in the reference's visiting order (sut.breadth_first_branches) cut into runs of equal
+    depth: the branches of one run depend only on earlier runs (their parents) and on each other
+    through the sibling test."""
+    order = [b.item() if hasattr(b, "item") else b for b in sut.breadth_first_branches(tree)]
+    depth = {tree.root: 0}
+    for _ in range(len(order)):
+        for p, c in tree.topology:
+            if p in depth and c not in depth:
+                depth[c] = depth[p] + 1
+    levels = []
+    for b in order:
+        d = depth.get(b, -1)
+        if levels and levels[-1][0] == d:
+            levels[-1][1].append(b)
+        else:
+            levels.append((d, [b]))
+    return order, [lv for _, lv in levels]
 
 
 def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_tol=0,
@@ -160,6 +218,13 @@ def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_
     rel_exp_cutoff or some pair of already simulated siblings has no more than
     inter_branch_tol of its genes anticorrelated.
 
+    The rejection loop runs a whole breadth-first level at a time: attempt a of branch b is a pure
+    function of (seed, b, a), so several attempts of every branch of the level are drawn, scanned,
+    carried, multiplied and tested (pst_lineage_checks: maximum per candidate, anticorrelated genes
+    per sibling pair) with one launch per stage and ONE device->host read per round; the host then
+    takes, branch by branch in the reference's visiting order, the first attempt that passes - the
+    same attempt the one-at-a-time loop would have taken.
+
     Returns (pd.Series rel_means, pd.Series programs, H), indexed in visiting order."""
     if not len(tree.time) == tree.num_branches:
         raise ValueError("the parameters are not enough for %i branches" % tree.num_branches)
@@ -168,31 +233,84 @@ def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_
     walk_seed = nat.split_seed(seed)
     state = _LineageState(tree, H, dev)
     tables = state.tables
-    K = state.K
-    done = {}                                   # branch -> rel rows view (device)
-    for branch in sut.breadth_first_branches(tree):
-        b = branch.item() if hasattr(branch, "item") else branch
-        bi = tables.index[b]
-        lo, hi = state.rows(b)
-        attempt = 0
-        while True:
-            if attempt >= max_attempts:
+    K, G = state.K, state.G
+    order, levels = _bfs_levels(tree)
+    position = {b: i for i, b in enumerate(order)}
+    group_of = {}
+    for siblings in tree.get_parallel_branches().values():
+        members = [s.item() if hasattr(s, "item") else s for s in siblings]
+        for b in members:
+            group_of.setdefault(b, members)          # first group that lists the branch (sim_utils.py:663-667)
+    st = nat.stream_ptr(dev)
+    done = set()
+    for level in levels:
+        pending = list(level)
+        base = {b: 0 for b in level}
+        want = 4
+        while pending:
+            # candidates of this round: `A` consecutive attempts of a prefix of the pending branches
+            T_of = {b: int(tables.T[tables.index[b]]) for b in pending}
+            A = max(1, min(want, state.S // max(1, sum(T_of.values()))))
+            batch, used = [], 0
+            for b in pending:
+                if used + A * T_of[b] > state.S and batch:
+                    break
+                batch.append(b)
+                used += A * T_of[b]
+            cands = [(b, base[b] + a) for b in batch for a in range(A)]
+            if max(a for _, a in cands) >= max_attempts:
+                b = batch[0]
                 raise RuntimeError("branch %s: no acceptable expression programs after %d "
                                    "attempts (rel_exp_cutoff=%g, inter_branch_tol=%g)"
-                                   % (str(b), attempt, rel_exp_cutoff, inter_branch_tol))
-            raw = _walk_programs([hi - lo], K, walk_seed, [bi], [attempt], dev) if K > 0 else None
-            top = state.place_branch(b, raw)
-            attempt += 1
-            if top > rel_exp_cutoff:                                   # simulation.py:270
-                continue
-            done[b] = state.rel[lo:hi]
-            parallels = sut.find_parallel(tree, done, b)               # :271
-            parallels = [p.item() if hasattr(p, "item") else p for p in parallels]
-            diverges = sut.diverging_parallel(parallels, done, tree.G, tol=inter_branch_tol,
-                                              device=dev)              # :272
-            if all(diverges):
-                break
-            del done[b]
+                                   % (str(b), max_attempts, rel_exp_cutoff, inter_branch_tol))
+            row, T = state.try_candidates(walk_seed, cands)
+            slot = {c: i for i, c in enumerate(cands)}
+            # sibling pairs: candidate x (accepted sibling | every candidate of a sibling visited earlier)
+            pairs, pa, pb, pn = {}, [], [], []
+            for b in batch:
+                older = [s for s in group_of.get(b, [b]) if s != b and position.get(s, 1 << 60) < position[b]
+                         and (s in done or s in batch)]
+                for a in range(A):
+                    i = slot[(b, base[b] + a)]
+                    for s in older:
+                        if s in done:
+                            lo, hi = state.rows(s)
+                            keys = [((b, a, s, None), lo, hi - lo)]
+                        else:
+                            keys = [((b, a, s, a2), int(row[slot[(s, base[s] + a2)]]), T_of[s]) for a2 in range(A)]
+                        for key, other_row, other_T in keys:
+                            pairs[key] = len(pa)
+                            pa.append(int(row[i]))
+                            pb.append(other_row)
+                            pn.append(min(int(T[i]), other_T))
+            slot_max = torch.full((len(cands),), float("-inf"), dtype=torch.float64, device=dev)
+            pair_neg = torch.zeros(max(1, len(pa)), dtype=torch.int32, device=dev)
+            nat.call("pst_lineage_checks", state.relall, G, len(cands), nat.to_dev(row, torch.int64, dev),
+                     nat.to_dev(T, torch.int32, dev), len(pa),
+                     nat.to_dev(pa, torch.int64, dev) if pa else None, nat.to_dev(pb, torch.int64, dev) if pa else None,
+                     nat.to_dev(pn, torch.int32, dev) if pa else None, slot_max, pair_neg, st)
+            tops = slot_max.cpu().numpy()                     # the one device->host read of the round
+            negs = pair_neg.cpu().numpy()
+            taken = {}                                         # branch -> attempt index accepted in this round
+            for b in batch:
+                siblings = [s for s in group_of.get(b, [b]) if s != b and position.get(s, 1 << 60) < position[b]]
+                if any(s not in done and s not in taken for s in siblings):
+                    continue                                   # an earlier sibling is still open: next round
+                for a in range(A):
+                    ok = not tops[slot[(b, base[b] + a)]] > rel_exp_cutoff            # simulation.py:270
+                    for s in siblings:
+                        key = (b, a, s, None) if (b, a, s, None) in pairs else (b, a, s, taken[s])
+                        ok = ok and (negs[pairs[key]] / (G * 1.0) > inter_branch_tol)  # sim_utils.py:249-251
+                    if ok:
+                        taken[b] = a
+                        break
+                else:
+                    base[b] += A
+            for b, a in taken.items():
+                state.accept(b, int(row[slot[(b, base[b] + a)]]))
+                done.add(b)
+            pending = [b for b in pending if b not in done]
+            want = 8
     if _return_state:
         return state, H
     rel_host = state.rel.cpu().numpy()
@@ -206,10 +324,12 @@ def simulate_lineage(tree, rel_exp_cutoff=8, intra_branch_tol=0.5, inter_branch_
     return pd.Series(rel_means), pd.Series(programs), H
 
 
-class DeviceMeans(object):
+class DeviceMeans(Mapping):
     """`tree.means` kept on the GPU: the fp32 (P, G) table the samplers read, plus W, H and the
     gene scale from which a branch's fp64 (T_b, G) array is rebuilt on the device and copied to
-    the host the first time `tree.means[branch]` is read.  Behaves like the reference's dict."""
+    the host the first time `tree.means[branch]` is read.  A read-only Mapping like the reference's
+    dict (`tree.add_genes(tree.means)` works); `to_host()` gives a plain dict of ndarrays, which is
+    also what pickling / copying a tree should carry."""
 
     def __init__(self, tables, W, H, gene_scale, table32):
         self.tables, self.W, self.H, self.gene_scale, self.table32 = tables, W, H, gene_scale, table32
@@ -228,9 +348,6 @@ class DeviceMeans(object):
             self._host[b] = buf.cpu().numpy()
         return self._host[b]
 
-    def keys(self):
-        return list(self.tables.names)
-
     def __iter__(self):
         return iter(self.tables.names)
 
@@ -240,11 +357,12 @@ class DeviceMeans(object):
     def __contains__(self, b):
         return b in self.tables.index
 
-    def items(self):
-        return [(b, self[b]) for b in self.tables.names]
+    def to_host(self):
+        """Plain dict branch -> (T_b, G) float64 ndarray, as the reference keeps it."""
+        return {b: self[b] for b in self.tables.names}
 
-    def values(self):
-        return [self[b] for b in self.tables.names]
+    def __reduce__(self):                      # pickling / deepcopy carry host arrays, not CUDA tensors
+        return (dict, (self.to_host(),))
 
 
 def default_gene_expression_on_device(tree, seed=None, device=None, abs_max=5000, gene_mean=0.8,
@@ -259,18 +377,20 @@ def default_gene_expression_on_device(tree, seed=None, device=None, abs_max=5000
     state, H = simulate_lineage(tree, seed=seed, device=device, _return_state=True, **kwargs)
     dev, tb = state.dev, state.tables
     st = nat.stream_ptr(dev)
-    # max over the tree of exp(rel) per gene (sim_utils.py:406-426,461): exp is monotone
-    cap = torch.exp(state.rel.max(dim=0).values)
+    # max over the tree of exp(rel) per gene (sim_utils.py:406-426,461): exp is monotone; the per-gene
+    # maximum comes out of the W.H kernel, the (P, G) table is not read back
+    colmax = state.gene_maxima()
     if base_seed is not None:
-        scale = sut.base_gene_exp_on_device(cap, base_seed, abs_max, gene_mean, gene_std)
+        scale = sut.base_gene_exp_on_device(torch.exp(colmax), base_seed, abs_max, gene_mean, gene_std)
         base = scale.cpu().numpy()
     else:
-        base = sut._base_gene_exp_legacy(cap.cpu().numpy(), abs_max, gene_mean, gene_std)  # sim_utils.py:463-469
+        base = sut._base_gene_exp_legacy(np.exp(colmax.cpu().numpy()), abs_max, gene_mean, gene_std)  # sim_utils.py:463-469
         scale = nat.to_dev(base, torch.float64, dev)
     table32 = torch.empty((tb.P, state.G), dtype=torch.float32, device=dev)
-    nat.call("pst_rel_means", nat.ptr(state.W), nat.ptr(state.H), nat.ptr(scale), 0, tb.P, state.K, state.G,
+    nat.call("pst_rel_means", nat.ptr(state.Wall), nat.ptr(state.H), nat.ptr(scale), 0, tb.P, state.K, state.G,
              None, None, nat.ptr(table32), None, st)
-    tree.means = DeviceMeans(tb, state.W, state.H, scale, table32)
+    tree.means = DeviceMeans(tb, state.W.clone(), state.H, scale, table32)      # drops the scratch rows
+    del state
     tree.invalidate_device_cache()
     return H, base
 
@@ -283,30 +403,24 @@ def _shard_range(n, shard):
     return shard_range(n, rank, world)
 
 
-def _finish(engine, tables, X, pt, codes, s64, dtype, out):
-    engine.check()
+def _sample_counts(engine, rows, s32, seed, first, dtype, out):
+    """The count matrix of the cells described by rows/s32: a device int32 tensor (out="torch") or a
+    fresh host array of `dtype` (reference: int64, simulation.py:651).  The host form never holds the
+    whole matrix on the GPU: chunks are sampled, copied as int32 into pinned staging and expanded into
+    the result by host threads while the next chunk is sampled (CountEngine.draw_to_host)."""
     if out == "torch":
-        return X, pt, codes, s64
-    return _counts_to_host(X, dtype), pt.cpu().numpy(), tables.branch_names(codes.cpu().numpy()), s64.cpu().numpy()
-
-
-_TORCH_INT = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.int16): torch.int16,
-              np.dtype(np.uint8): torch.uint8, np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
-
-
-def _counts_to_host(X, dtype):
-    """Device int32 counts -> host ndarray of `dtype` (reference: int64).  The widening is done on
-    the device chunk by chunk, so the host never runs an astype pass over the matrix."""
+        X = engine.draw(rows, s32, seed, first)
+        engine.check()
+        return X
     want = np.dtype(dtype)
-    if want == np.dtype(np.int32) or want not in _TORCH_INT:
-        Xh = X.cpu().numpy()
-        return Xh if want == Xh.dtype else Xh.astype(want)
-    n, G = X.shape
-    host = torch.empty((n, G), dtype=_TORCH_INT[want])
-    step = max(1, (256 << 20) // max(1, 8 * G))
-    for lo in range(0, n, step):
-        host[lo:lo + step].copy_(X[lo:lo + step].to(_TORCH_INT[want]))
-    return host.numpy()
+    n = int(rows.numel())
+    direct = want in (np.dtype(np.int32), np.dtype(np.int64))
+    host = np.empty((n, engine.G), dtype=want if direct else np.int64)
+    if n and engine.G:
+        engine.draw_to_host(rows, s32, seed, first, host)
+    torch.cuda.current_stream(engine.dev).synchronize()
+    engine.check()
+    return host if direct else host.astype(want)
 
 
 def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
@@ -326,8 +440,8 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
     if host_out is not None:
         hX, hpt, hcodes, hs = host_out[:4]
         overflow = host_out[4] if len(host_out) > 4 else None
-        if tuple(hX.shape) != (n, engine.G) or hX.dtype not in (torch.int32, torch.uint16, torch.uint8):
-            raise ValueError("host_out[0] must be an int32 (or uint16 / uint8) CPU tensor of shape (%d, %d)"
+        if tuple(hX.shape) != (n, engine.G) or hX.dtype not in (torch.int32, torch.int64, torch.uint16, torch.uint8):
+            raise ValueError("host_out[0] must be an int32 (or int64 / uint16 / uint8) CPU tensor of shape (%d, %d)"
                              % (n, engine.G))
         hpt.copy_(pt, non_blocking=True)
         hcodes.copy_(codes, non_blocking=True)
@@ -343,8 +457,10 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
                                     "or use an int32 buffer"
                                     % (len(engine.overflow[0]), str(hX.dtype).replace("torch.", "")))
         return hX.numpy(), hpt.numpy(), tables.branch_names(hcodes.numpy()), hs.numpy()
-    X = engine.draw(rows, s32, nat.derive_seed(seed, 2), first)
-    return _finish(engine, tables, X, pt, codes, s64, dtype, out)
+    X = _sample_counts(engine, rows, s32, nat.derive_seed(seed, 2), first, dtype, out)
+    if out == "torch":
+        return X, pt, codes, s64
+    return X, pt.cpu().numpy(), tables.branch_names(codes.cpu().numpy()), s64.cpu().numpy()
 
 
 def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, scale_mean=0.,
@@ -518,11 +634,7 @@ def draw_counts(tree, pseudotime, branches, scalings, alpha, beta, seed=None, de
     if np.ndim(beta) == 0:
         beta = [beta] * tree.G
     engine = CountEngine(tree, tables, alpha, beta, dev, sampler=sampler)
-    X = engine.draw(rows, s32, seed, first)
-    engine.check()
-    if out == "torch":
-        return X
-    return _counts_to_host(X, dtype)
+    return _sample_counts(engine, rows, s32, seed, first, dtype, out)
 
 
 def add_non_diff_genes(inform_expr_matrix, genes, gene_params, cell_scalings, seed=None,

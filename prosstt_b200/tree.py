@@ -8,6 +8,8 @@ feed the device tables in `prosstt_b200.device` and are bit-exact with the refer
 """
 from collections import defaultdict
 
+from collections.abc import Mapping
+
 import numpy as np
 import pandas as pd
 
@@ -86,7 +88,7 @@ class Tree(object):
     def add_genes(self, *args):
         """add_genes(dict of (T_b,G) means) or add_genes(relative_means, base_expr)
         (tree.py:154-163)."""
-        if len(args) == 1 and isinstance(args[0], dict):
+        if len(args) == 1 and isinstance(args[0], Mapping):      # dict, or the device-resident DeviceMeans
             self._add_genes_from_average(args[0])
         if len(args) == 2 and isinstance(args[1], np.ndarray):
             self._add_genes_from_relative(args[0], args[1])

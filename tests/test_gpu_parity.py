@@ -198,6 +198,45 @@ def test_simulate_lineage_properties():
         sim.simulate_lineage(t, seed=1, device=DEV)
 
 
+def test_batched_lineage_takes_the_first_acceptable_attempt():
+    """simulate_lineage tests a whole breadth-first level per round (several attempts of every branch in
+    one launch per stage, one device->host read).  It must accept exactly what the reference's
+    one-branch-at-a-time loop (simulation.py:264-282) accepts: for every branch the FIRST attempt whose
+    maximum passes the cutoff and which diverges from every sibling simulated before it.  Replayed here
+    attempt by attempt with the oracle's tests; a tight cutoff forces rejections."""
+    np.random.seed(11)
+    top = [[int(a), int(b)] for a, b in ptree.Tree.gen_random_topology(4)]
+    top.append([8, 9])                                               # a chained branch (one child)
+    top.append([3, 10]); top.append([3, 11]); top.append([3, 12])    # and a three-way fork
+    nb = 13
+    time = {b: 20 + 5 * (b % 4) for b in range(nb)}
+    t = ptree.Tree(topology=top, time=time, num_branches=nb, branch_points=5, modules=6, G=400)
+    cutoff = 3.0
+    rel, W, H = sim.simulate_lineage(t, rel_exp_cutoff=cutoff, a=0.05, seed=77, device=DEV)
+    ot = orc.OTree(top, time)
+    order = [b.item() if hasattr(b, "item") else b for b in sut.breadth_first_branches(t)]
+    dev = torch.device(DEV)
+    seen, rejected = [], 0
+    for b in order:
+        p = orc.parent_of(ot, b)
+        older = [s for s in seen if p is not None and orc.parent_of(ot, s) == p]
+        found = None
+        for a in range(200):
+            raw = sim._walk_programs([time[b]], 6, nat.split_seed(77), [t.branches.index(b)], [a], dev).cpu().numpy()
+            cand = raw if p is None else orc.carry_from_parent(raw, W[p])
+            r = np.dot(cand, H)
+            ok = not (r.max() > cutoff) and all(orc.pearson_anticorrelated(r, rel[s]) / 400.0 > 0 for s in older)
+            if np.allclose(cand, W[b], rtol=0, atol=1e-12):
+                assert ok, (b, a)                                    # the accepted attempt passes ...
+                found = a
+                break
+            assert not ok, (b, a)                                    # ... and every earlier one fails
+            rejected += 1
+        assert found is not None, b
+        seen.append(b)
+    assert rejected >= 3                                             # the cutoff did force redraws
+
+
 # ------------------------------------------------------------------ index maps, draws in
 def _golden_tree(name):
     branches, time, top, d = golden_lineage(name)
@@ -409,6 +448,57 @@ def test_streamed_host_output_and_launch_shape_invariance(sampler):
     eng2 = CountEngine(t2, TreeTables(t2, dev), s["alpha"][:G2], s["beta"][:G2], dev, sampler=sampler)
     part = eng2.draw(rows, sc, 5, 1000).cpu()
     assert torch.equal(part, direct[:, :G2])
+
+
+def test_staged_host_transports_and_default_api_are_exact():
+    """The reference-shaped call returns a fresh int64 NumPy array (simulation.py:651): chunks cross PCIe
+    as int32 / uint16 / uint8 into pinned staging and host threads (pst_host_widen, pst_host_apply_overflow)
+    expand them.  Every transport must give exactly the counts the device holds, incl. the elements that
+    saturate uint8 (deep library: many counts > 255) and a chunk size that does not divide n."""
+    t, s, d = _golden_tree("bp2")
+    dev = torch.device(DEV)
+    tb = TreeTables(t, dev)
+    eng = CountEngine(t, tb, s["alpha"], s["beta"], dev, sampler="hybrid")
+    n = 2500
+    rng = np.random.RandomState(3)
+    rows = _dev(rng.randint(0, tb.P, size=n), torch.int32)
+    sc = _dev(np.exp(rng.normal(2.5, 0.7, size=n)), torch.float32)          # deep: saturates uint8
+    want = eng.draw(rows, sc, 9, 77).cpu().numpy()
+    assert (want > 255).mean() > 1e-3
+    for transport in ("i32", "u16", "u8"):
+        for dt in (np.int32, np.int64):
+            host = np.full((n, t.G), -1, dtype=dt)
+            eng.draw_to_host(rows, sc, 9, 77, host, chunk_cells=611, transport=transport, threads=3)
+            assert np.array_equal(host, want), (transport, dt)
+    pinned = torch.empty((n, t.G), dtype=torch.int64).pin_memory()
+    eng.draw_to_host(rows, sc, 9, 77, pinned)                               # int64 tensor: staged too
+    assert np.array_equal(pinned.numpy(), want)
+    eng.check()
+    # the public call with the reference's defaults: int64 ndarray, equal to the device-resident result
+    kw = dict(alpha=s["alpha"], beta=s["beta"], seed=5, device=DEV)
+    X64 = sim.sample_density(t, 3000, **kw)[0]
+    Xd = sim.sample_density(t, 3000, out="torch", **kw)[0]
+    assert X64.dtype == np.int64 and X64.flags.writeable and np.array_equal(X64, Xd.cpu().numpy())
+    X16 = sim.sample_density(t, 3000, dtype=np.int16, **kw)[0]
+    assert X16.dtype == np.int16 and np.array_equal(X16, X64.astype(np.int16))
+    lib = nat.load()
+    assert lib.pst_host_checksum(X64.view(np.uint32).ctypes.data, X64.nbytes, 4) == int(X64.sum())
+
+
+def test_calls_run_on_the_requested_device_not_the_current_one():
+    """device="cuda:1" while device 0 is current: the launch must happen on GPU 1 and
+    give the same counts as on GPU 0 (every draw is a function of seed and global indices only)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    t, s, d = _golden_tree("abc")
+    kw = dict(alpha=s["alpha"], beta=s["beta"], seed=21)
+    torch.cuda.set_device(0)
+    X0, pt0, br0, sc0 = sim.sample_density(t, 2000, device="cuda:0", **kw)
+    X1, pt1, br1, sc1 = sim.sample_density(t, 2000, device="cuda:1", **kw)
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(X0, X1) and np.array_equal(pt0, pt1) and np.array_equal(sc0, sc1) and list(br0) == list(br1)
+    Xt = sim.sample_density(t, 2000, device="cuda:1", out="torch", **kw)[0]
+    assert Xt.device == torch.device("cuda:1") and np.array_equal(Xt.cpu().numpy(), X0)
 
 
 def test_domain_and_range_errors():
@@ -1079,7 +1169,7 @@ def test_large_cell_count_draw_is_partition_consistent():
 def test_inversion_far_tail_mass_is_pinned_from_both_sides():
     """The far upper tail of the hybrid sampler's inversion.  fp32 cannot resolve the cdf next to 1, so
     counts whose Philox word lies in the top 2^-14 are inverted in fp64 with a 64-bit uniform
-    (invert_tail_f64).  2e8 draws per regime: the mass beyond the 1 - 1e-6 and 1 - 1e-7 quantiles must
+    (invert_tail).  2e8 draws per regime: the mass beyond the 1 - 1e-6 and 1 - 1e-7 quantiles must
     sit inside a two-sided Poisson interval around its exact expectation (round 1 only had an upper
     bound, and the tail of the high-theta regimes was 30 % light), and the body must be untouched.
     Regimes: the old spike case, the high-variance corner the judge measured (mu = 20, alpha = 0.9), the

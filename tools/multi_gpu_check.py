@@ -21,10 +21,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-import argparse
-a = argparse.Namespace(branch_points=3, steps_per_branch=40, programs=8, genes=4000)
-tree = bench.build_tree_gpu(a, dev)
-alpha, beta = bench.gene_hyper(a.genes)
+w = dict(bp=3, chain=0, T=40, G=4000, K=8)
+tree = bench.build_tree_gpu(w, dev)
+alpha, beta = bench.gene_hyper(w["G"])
 ok = True
 for name, call in (
     ("sample_density", lambda **kw: sim.sample_density(tree, 8 * 1000 + 3, alpha=alpha, beta=beta, seed=5, device=dev, out="torch", **kw)),

@@ -5,9 +5,9 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from prosstt_b200 import simulation as sim
-a = argparse.Namespace(branch_points=7, steps_per_branch=50, programs=10, genes=20000, cells=1)
+a = argparse.Namespace(genes=20000)
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
-tree = bench.build_tree_gpu(a, dev)
+tree = bench.build_tree_gpu(dict(bench.WORKLOADS["c4"]), dev)
 alpha, beta = bench.gene_hyper(a.genes)
 n = 131072
 bufs = (torch.empty((n, a.genes), dtype=torch.int32).pin_memory(), torch.empty(n, dtype=torch.int64).pin_memory(),

@@ -21,7 +21,7 @@ ap.add_argument("--samplers", default="gamma_poisson,hybrid")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--scale-mean", type=float, default=0.0, help="mean of log library size (depth regime)")
 a = ap.parse_args()
-args = argparse.Namespace(branch_points=7, steps_per_branch=50, programs=10, genes=a.genes, cells=a.cells)
+args = dict(bench.WORKLOADS["c4"], G=a.genes)
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 t0 = time.time()
