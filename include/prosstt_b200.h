@@ -175,17 +175,19 @@ int pst_nb_params(const double *alpha, const double *beta, const double *mu,
                   int64_t n_cells, int64_t G, double *out_p, double *out_r, void *stream);
 
 /* The SAME parameterisation in fp32, evaluated by the __device__ functions that pst_draw_counts
- * inlines (MUFU rcp/lg2, the small-theta series): for element i with mean mu[i] and per-element
- * alpha[i], beta_m1[i] = beta-1 it writes theta = alpha mu + beta - 1 (gamma scale; scipy's
- * p = 1/(1+theta)), r = mu/theta (gamma shape, scipy's n), q = theta/(1+theta) = get_pr_umi's p,
- * a = q r, log2 P(X=0) = -r log2(1+theta), and the route the hybrid sampler takes.  Parity hook
- * on the arithmetic that actually runs (count_model.py:156-161). */
+ * inlines (MUFU rcp/lg2, the small-theta series), in the same operation order: element i has the
+ * means-table value M[i], library size scaling[i] and per-element alpha[i], beta_m1[i] = beta-1.
+ * Outputs: mu = M s, theta = (alpha M) s + beta-1 (gamma scale; scipy's p = 1/(1+theta)), r = mu/theta
+ * (gamma shape, scipy's n), q = theta/(1+theta) = get_pr_umi's p, a = q r, log2 P(X=0) =
+ * -r log2(1+theta), and the route the hybrid sampler takes.  Parity hook on the arithmetic that
+ * actually runs (count_model.py:156-161). */
 #define PST_ROUTE_MIXTURE       0   /* gamma-Poisson mixture                                  */
-#define PST_ROUTE_INVERSION     1   /* inversion of the NB cdf (mean <= 32, sd <= 20, shape <= 48 or theta < 0.1) */
+#define PST_ROUTE_INVERSION     1   /* inversion of the NB cdf: mean <= 32, sd <= 20, theta <= 32, shape <= 48
+                                       (or theta < 0.1), decided as s <= s_max(M, alpha, beta-1) */
 #define PST_ROUTE_DOMAIN_ERROR  2   /* sets PST_FLAG_DOMAIN in the sampler                    */
-int pst_nb_params_f32(const float *mu, const float *alpha, const float *beta_m1, int64_t n,
-                      float *out_theta, float *out_r, float *out_q, float *out_a,
-                      float *out_log2p0, int32_t *out_route, void *stream);
+int pst_nb_params_f32(const float *M, const float *scaling, const float *alpha, const float *beta_m1,
+                      int64_t n, float *out_mu, float *out_theta, float *out_r, float *out_q,
+                      float *out_a, float *out_log2p0, int32_t *out_route, void *stream);
 
 /* ---- the hot loop: draw_counts, simulation.py:602-651 ------------------------- */
 /* X[i][g] ~ NB(mean mu = means[row_of_cell[i]][g]*scaling[i],
@@ -198,28 +200,26 @@ int pst_nb_params_f32(const float *mu, const float *alpha, const float *beta_m1,
  * elements (>= G).  flags: FOUR uint32 words, zeroed once by the caller: word 0 is OR-ed
  * with PST_FLAG_*; words 1-3 are reserved (the work-scheduler words live in the library,
  * one set per (device, stream), so concurrent launches on different streams are safe).
- * cell_order (optional, may be NULL): a permutation of [0,n) giving the order in which the
- * cells are visited (hybrid sampler only; see pst_group_cells_by_row).
- * scratch (hybrid sampler only; NULL otherwise): pst_draw_scratch_words(n, G) uint32 words,
- * 16-byte aligned, private to this call until it has completed.  It receives the list of the
- * counts whose uniform lies in the top 2^-14 (about 6e-5 n G entries of 16 bytes); a second
- * small kernel inverts those in fp64 with a 64-bit uniform, which is what resolves the upper
- * tail beyond the 1 - 1e-7 quantile.  Content on entry is ignored. */
-int64_t pst_draw_scratch_words(int64_t n, int64_t G);
+ * scratch: pst_draw_scratch_words(n, G, P) uint32 words, 16-byte aligned, private to this call
+ * until it has completed; content on entry is ignored.  It holds (a) the visiting order of the
+ * cells - grouped by tree row (counting sort) and cut into groups of at most 64 cells of one row,
+ * so that everything depending on (row, gene) is formed once per group and concurrently running
+ * warps share means rows; built by four small kernels in front of the draw, it never changes the
+ * counts - and (b) the list of the counts whose uniform lies in the top 2^-14 (about 6e-5 n G
+ * entries of 16 bytes), which a last small kernel inverts with a 64-bit uniform against a cdf
+ * accumulated in fp64: that is what resolves the upper tail beyond the 1 - 1e-7 quantile. */
+int64_t pst_draw_scratch_words(int64_t n, int64_t G, int64_t P);
+/* Word offsets inside that scratch (debugging / tests): h_out[0] = capacity of the tail list (entries
+ * of 4 words from word 4; word 0 counts them), [1] = order[n] (cells in visiting order), [2] =
+ * bins[P+1], [3] = gstart[P+1], [4] = groups (4 words each: first position in order, cells, tree row,
+ * 0; word 1 of the scratch counts them), [5] = most groups the layout has room for. */
+int pst_draw_scratch_layout(int64_t n, int64_t G, int64_t P, int64_t *h_out);
 int pst_draw_counts(const float *means, int64_t P, int64_t G,
                     const int32_t *row_of_cell, const float *scaling,
                     const float *alpha, const float *beta_m1,
                     uint64_t seed, int64_t cell0, int64_t n,
                     int32_t *X, int64_t ldx, uint32_t *flags, int32_t sampler,
-                    const int32_t *cell_order, uint32_t *scratch, int64_t scratch_words,
-                    void *stream);
-
-/* Counting sort of the cells by tree row: order[] lists the cells of row 0, then row 1, ...
- * (arbitrary order inside a row).  bins: P uint32 words of scratch.  Feeding `order` to
- * pst_draw_counts makes concurrently running warps share means rows (L2/L1 hits instead of
- * DRAM re-reads); it never changes the counts. */
-int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int32_t P,
-                           uint32_t *bins, int32_t *order, void *stream);
+                    uint32_t *scratch, int64_t scratch_words, void *stream);
 
 /* One streaming pass over a count matrix X[n][ldx] (first G columns): per-cell total counts and
  * zero counts, per-gene sum, sum of squares and zero counts.  These are the summaries the

@@ -41,22 +41,24 @@ def get_pr_umi(a, b, m, device=None):
     return d_p.cpu().numpy().reshape(m_arr.shape), d_r.cpu().numpy().reshape(m_arr.shape)
 
 
-def sampler_params_f32(a, b, m, device=None):
+def sampler_params_f32(a, b, m, scaling=1.0, device=None):
     """The fp32 parameterisation exactly as the count sampler evaluates it (pst_nb_params_f32 runs
-    the __device__ functions that pst_draw_counts inlines): dict of theta = a m + b - 1, r = m/theta
-    (scipy's n), q = theta/(1+theta) (get_pr_umi's p), a = q r, log2p0 = log2 P(X = 0) and route
-    (0 mixture, 1 inversion, 2 domain error).  a, b, m broadcast to a common 1-d shape."""
+    the __device__ functions that pst_draw_counts inlines, in the same order): for means-table
+    values m, library sizes `scaling` and variance parameters a, b (broadcast to a common shape) a dict
+    of mu = m s, theta = (a m) s + b - 1, r = mu/theta (scipy's n), q = theta/(1+theta) (get_pr_umi's p),
+    a = q r, log2p0 = log2 P(X = 0) and route (0 mixture, 1 inversion, 2 domain error)."""
     dev = nat.device(device)
-    m_arr, a_arr, b_arr = np.broadcast_arrays(np.asarray(m, np.float64), np.asarray(a, np.float64),
-                                              np.asarray(b, np.float64))
+    m_arr, s_arr, a_arr, b_arr = np.broadcast_arrays(np.asarray(m, np.float64), np.asarray(scaling, np.float64),
+                                                     np.asarray(a, np.float64), np.asarray(b, np.float64))
     shape = m_arr.shape
     n = int(m_arr.size)
     d_m = nat.to_dev(m_arr.ravel(), torch.float32, dev)
+    d_s = nat.to_dev(s_arr.ravel(), torch.float32, dev)
     d_a = nat.to_dev(a_arr.ravel(), torch.float32, dev)
     d_b = nat.to_dev((b_arr - 1.0).ravel(), torch.float32, dev)       # beta-1 formed in fp64 like gene_params
-    outs = {k: torch.empty(n, dtype=torch.float32, device=dev) for k in ("theta", "r", "q", "a", "log2p0")}
+    outs = {k: torch.empty(n, dtype=torch.float32, device=dev) for k in ("mu", "theta", "r", "q", "a", "log2p0")}
     route = torch.empty(n, dtype=torch.int32, device=dev)
-    nat.call("pst_nb_params_f32", d_m, d_a, d_b, n, outs["theta"], outs["r"], outs["q"], outs["a"],
+    nat.call("pst_nb_params_f32", d_m, d_s, d_a, d_b, n, outs["mu"], outs["theta"], outs["r"], outs["q"], outs["a"],
              outs["log2p0"], route, nat.stream_ptr(dev))
     res = {k: v.cpu().numpy().reshape(shape) for k, v in outs.items()}
     res["route"] = route.cpu().numpy().reshape(shape)

@@ -107,6 +107,7 @@ __device__ __forceinline__ double normal_f64(uint4 r) {
 // fast reciprocal / base-2 log / exp (one MUFU each, no slow-path branches)
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ---------------------------------------------------------------------------
@@ -135,16 +136,37 @@ __device__ __forceinline__ void nb_inversion_params(float mu, float th, float &q
   if (th < kSmallTheta) e2 = nb_log2p0_small_theta(mu, th);
 }
 // Which counts the hybrid sampler inverts (the rest goes to the gamma-Poisson mixture): a function of
-// the parameters only.  mean <= 32 and sd <= 20 bound the length of a search; shape r <= 48 (or the
-// small-theta series) bounds the error of log2 P(0): r |d lg2| <= 48 (2^-22 + 2^-24/ln 2) = 1.6e-5.
-constexpr float kInvMuMax = 32.0f, kInvVarMax = 400.0f, kInvShapeMax = 48.0f;
-__device__ __forceinline__ bool nb_shape_ok(float th, float q, float a) {     // r = a/q <= 48, or the series
-  return (a <= kInvShapeMax * q) || (th < kSmallTheta);
+// the parameters only, never of the uniforms.
+//   mean mu <= 32 and variance mu (1+theta) <= 400   bound the length of a search;
+//   shape r <= 48 (or theta < 0.1, the series)        bounds the error of log2 P(0): r |d lg2| <= 48 (2^-22 +
+//                                                     2^-24/ln 2) = 1.6e-5, inside the 2^-15 stretch;
+//   theta <= 32                                       keeps the tail ratio q below 0.97, so that below the
+//                                                     1 - 2^-14 quantile (where the 24-bit fp32 uniform decides)
+//                                                     no bin is narrower than ~30 steps of the uniform.
+// For a given tree row and gene, mu = M s and theta = alpha M s + (beta-1) grow with the library size s,
+// and so do the variance and the shape: the four conditions hold exactly for s <= s_max(M, alpha, beta-1).
+// The draw kernel forms s_max once per (chunk, gene) and routes every count with ONE comparison.
+// Genes whose parameters are not all positive and finite get s_max = -1: their counts go to the mixture
+// queue, whose drain checks the domain (mu > 0, theta > 0) and reports scipy's "Domain error".
+constexpr float kInvMuMax = 32.0f, kInvVarMax = 400.0f, kInvShapeMax = 48.0f, kInvThetaMax = 32.0f;
+__device__ __forceinline__ float nb_inversion_s_max(float M, float alpha, float bm) {
+  if (!(M > 0.f && M < 3.0e38f && alpha >= 0.f && alpha < 3.0e38f && bm > 0.f && bm < 3.0e38f)) return -1.f;
+  const float c = alpha * M;                               // theta = c s + bm
+  const float b1 = (1.0f + bm) * M;                        // variance = c M s^2 + b1 s
+  const float inf = __int_as_float(0x7f800000);
+  // (MUFU reciprocals / square root: the thresholds need to be deterministic, not correctly rounded)
+  const float rc = rcp_fast(c);                                                    // +inf for c = 0
+  float s = kInvMuMax * rcp_fast(M);                                               // mean <= 32
+  s = fminf(s, 2.0f * kInvVarMax * rcp_fast(b1 + sqrt_fast(fmaf(b1, b1, 4.0f * kInvVarMax * c * M))));   // variance <= 400
+  if (c > 0.f) s = fminf(s, (kInvThetaMax - bm) * rc);                             // theta <= 32
+  else if (bm > kInvThetaMax) s = -1.f;
+  // shape r = M s / (c s + bm) <= 48  <=>  s (M - 48 c) <= 48 bm;  or theta < 0.1  <=>  s < (0.1 - bm)/c
+  const float s_shape = (M > kInvShapeMax * c) ? kInvShapeMax * bm * rcp_fast(M - kInvShapeMax * c) : inf;
+  const float s_series = (bm < kSmallTheta) ? (c > 0.f ? (kSmallTheta - bm) * rc : inf) : -1.f;
+  return fminf(s, fmaxf(s_shape, s_series));
 }
-__device__ __forceinline__ bool nb_route_inversion(float mu, float th, float q, float a, float mu_max = kInvMuMax,
-                                                   float var_max = kInvVarMax) {
-  return (mu > 0.f) && (mu <= mu_max) && (th > 0.f) && (mu * (1.0f + th) <= var_max) &&
-         nb_shape_ok(th, q, a);                            // comparisons are false on NaN
+__device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
+  return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
 }
 
 // L2 residency hints: the means table is re-read by every cell (keep), X is written once (stream)

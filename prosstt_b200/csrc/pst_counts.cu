@@ -138,9 +138,6 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   return MixResult{k, MIX_DONE};
 }
 
-__device__ __forceinline__ bool nb_domain_ok(float mu, float theta) {
-  return (mu > 0.f) && (theta > 0.f) && (theta < 3.0e38f) && (mu < 3.0e38f);
-}
 
 // ---------------------------------------------------------------------------
 // kernel "hybrid": distribution-identical, divergence-aware, warp-autonomous.
@@ -265,38 +262,53 @@ __device__ __forceinline__ int invert_tail(float mu, float th, uint32_t key0, ui
 // slot per (device, stream), see sched_slot().  Zero between launches (the last warp rearms them).
 __device__ unsigned int g_sched[PST_SCHED_SLOTS][2];
 
+constexpr int HY_MCAP = HY_QCAP;             // mixture queue: 31 carried + 128 new
+constexpr int HY_LCAP = 40;                  // long searches: a full batch plus the few a drained batch adds
 struct HyWarpQueues {
   float4 se[HY_QCAP];       // inversion tail: t = P(k) k! at k = KFIX-1, cdf(k)-u, a, q
   int2 sw[HY_QCAP];         //                 where the count goes: (cell, gene)
-  float4 ge[HY_QCAP];       // mixture: mu (or lambda once the gamma is accepted), theta, cell, gene
-  int ga[HY_QCAP];          //          attempt counter of the current stage | stage << 16
-  float4 mstage[32];        // next cell's means quad, filled by cp.async (one slot per lane)
+  float4 le[HY_LCAP];       // long searches (still open after stage 2): P(k), cdf(k)-u, a + q k, q at k = HY_TAIL0
+  int2 lw[HY_LCAP];         //                 where the count goes
+  float4 ge[HY_MCAP];       // mixture: mu (or lambda once the gamma is accepted), theta, cell, gene
+  int ga[HY_MCAP];          //          attempt counter of the current stage | stage << 16
+  int fill[4];              // [0] search entries (appended with shared-memory atomics), [1] long searches
 };
 
 #ifndef HY_MIN_CTAS
-#define HY_MIN_CTAS 7     // 28 warps/SM: up to 72 registers (69 used) and 29.5 KB of queues per CTA
+#define HY_MIN_CTAS 7     // 28 warps/SM: up to 72 registers and 29.6 KB of queues per CTA
 #endif
-constexpr int HY_CHUNK_CELLS = 64;           // cells per chunk (x 32 quads = 8192 counts)
+#ifndef HY_ENQ_ATOMIC
+#define HY_ENQ_ATOMIC 1   // search-queue slots from a shared-memory counter (1) or from ballots (0)
+#endif
+#ifndef HY_CHUNK_CELLS
+#define HY_CHUNK_CELLS 64                    // most cells per chunk (x 32 quads = 8192 counts); all of one tree row
+#endif
 
+// Work decomposition.  The cells of a launch are visited grouped by tree row (counting sort,
+// group_* kernels below): a GROUP is a run of at most HY_CHUNK_CELLS cells that share their row, a
+// CHUNK is one group times one strip of 32 gene quads (one quad per lane, 128 genes = 512 contiguous
+// bytes of each X row).  Inside a chunk everything that depends on (row, gene) is constant:
+// the means quad M, c = alpha M, beta-1 and the largest library size s for which the gene is routed to
+// the inversion (nb_inversion_s_max) are formed once per chunk; per cell only its id and its library
+// size s are read (by the lanes, 32 cells per request, broadcast with shuffles), mu = M s,
+// theta = c s + beta-1, and the route is one comparison s <= s_max.  Chunks are handed out by an
+// atomic counter, so warps whose queues drain more often simply take fewer of them; consecutive
+// chunk ids are adjacent strips of the same cells (neighbouring warps complete the same X rows
+// together), and concurrently running warps share means rows in L2.
 template <int KFIX, bool VEC, bool ALL_MIX>
 __global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
-draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, uint32_t P,
-                          uint32_t G, uint32_t Q, const int32_t *__restrict__ row_of_cell,
-                          const float *__restrict__ scaling, const float *__restrict__ alpha,
-                          const float *__restrict__ beta_m1, int64_t cell0, int64_t n,
-                          int32_t *__restrict__ X, uint32_t ldx, uint32_t *__restrict__ flags,
-                          const int32_t *__restrict__ cell_order, float mu_max_arg, float var_max_arg,
-                          int sched, uint32_t *__restrict__ tail, uint32_t tail_cap) {
-#ifdef PST_DEV_KNOBS
-  const float mu_max = mu_max_arg, var_max = var_max_arg;
-#else
-  constexpr float mu_max = HY_MU_MAX, var_max = HY_VAR_MAX;      // immediates in the route test
-#endif
+draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, uint32_t G, uint32_t Q,
+                   const float *__restrict__ scaling, const float *__restrict__ alpha,
+                   const float *__restrict__ beta_m1, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx,
+                   uint32_t *__restrict__ flags, const uint32_t *__restrict__ hdr,
+                   const int32_t *__restrict__ order, const uint4 *__restrict__ groups, int sched,
+                   uint32_t *__restrict__ tail, uint32_t tail_cap) {
   __shared__ HyWarpQueues queues[HY_WARPS];
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * (int64_t)((Q + 31u) / 32u);
+  const uint32_t n_strips = (Q + 31u) / 32u;
+  const uint64_t n_chunks = (uint64_t)hdr[1] * n_strips;      // hdr[1] = number of groups (group_table_kernel)
   const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
   const uint32_t key0 = key.k0[0], key1 = key.k1[0];
   constexpr float inv_fact[34] = PST_INV_FACT_TABLE;
@@ -304,26 +316,19 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
   int ns = 0, ng = 0;                         // queue fill, warp-uniform
   uint32_t flag = 0;
   const uint64_t keep = l2_policy_evict_last();
+  if (lane < 4) wq.fill[lane] = 0;
+  __syncwarp();
 
-  // finish up to 32 queued inversions at full warp width; k is warp-uniform
-  auto drain_search = [&](int first, int cnt) {
+
+  // the open-ended part of a search, 32 long searches at a time: P(k) form from k = HY_TAIL0, a + q k
+  // advanced by one FADD per term, 1/(k+1) from the constant bank, a vote every 4 terms
+  auto drain_long = [&](int first, int cnt) {
     const bool act = lane < cnt;
-    const int e = first + lane;
-    const float4 st = act ? wq.se[e] : make_float4(0.f, 1.f, 0.f, 0.f);
-    float tt = st.x, dd = st.y;                            // t = P(KFIX-1) (KFIX-1)!
-    const float aa = st.z, qq = st.w;
-    int cn = KFIX;
-    // second stage: HY_STAGE2 further terms in the head's form t_k = P(k) k! with compile-time k
-    // (4 instructions per term instead of 8 in the generic loop below)
-#pragma unroll
-    for (int s2 = 0; s2 < HY_STAGE2; ++s2) {
-      const int k = KFIX - 1 + s2;
-      tt = inv_t_next(tt, aa, qq, k);                        // t_{k+1}
-      dd = fmaf(tt, inv_fact[k + 1], dd);                    // cdf(k+1) - u
-      cn += (int)(__float_as_uint(dd) >> 31);
-    }
-    float pp = tt * inv_fact[KFIX - 1 + HY_STAGE2];          // back to P(k) for the open-ended loop
-    float ak = fmaf(qq, (float)(KFIX - 1 + HY_STAGE2), aa);  // a + q k, advanced by one FADD per term
+    const float4 st = act ? wq.le[first + lane] : make_float4(0.f, 1.f, 0.f, 0.f);
+    const int2 w = act ? wq.lw[first + lane] : make_int2(0, 0);
+    float pp = st.x, dd = st.y, ak = st.z;
+    const float qq = st.w;
+    int cn = KFIX + HY_STAGE2;
     for (int it = 0; it < HY_KMAX / 4; ++it) {
       if (!__any_sync(0xffffffffu, dd < 0.f)) break;          // every cdf has passed its u
       float rk[4];
@@ -344,8 +349,47 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     }
     // every u handled here lies below 1 - 2^-15 < T, the top of the computed cdf, and cdf - u is
     // accumulated (exact near the crossing), so each search ends; HY_KMAX only bounds the loop
-    const int2 w = act ? wq.sw[e] : make_int2(0, 0);
     if (act) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
+  };
+  // finish up to 32 queued inversions at full warp width; k is warp-uniform
+  auto drain_search = [&](int first, int cnt) {
+    const bool act = lane < cnt;
+    const int e = first + lane;
+    const float4 st = act ? wq.se[e] : make_float4(0.f, 1.f, 0.f, 0.f);
+    float tt = st.x, dd = st.y;                            // t = P(KFIX-1) (KFIX-1)!
+    const float aa = st.z, qq = st.w;
+    int cn = KFIX;
+    // second stage: HY_STAGE2 further terms in the head's form t_k = P(k) k! with compile-time k
+    // (4 instructions per term instead of 8 in the generic loop below)
+#pragma unroll
+    for (int s2 = 0; s2 < HY_STAGE2; ++s2) {
+      const int k = KFIX - 1 + s2;
+      tt = inv_t_next(tt, aa, qq, k);                        // t_{k+1}
+      dd = fmaf(tt, inv_fact[k + 1], dd);                    // cdf(k+1) - u
+      cn += (int)(__float_as_uint(dd) >> 31);
+    }
+    const int2 w = act ? wq.sw[e] : make_int2(0, 0);
+    // Searches still open after stage 2 (about 6 % of the entries, but 86 % of the batches hold one) move on
+    // to the queue of long searches, which is drained 32 at a time: the open-ended loop then runs at full
+    // width instead of once per batch for one or two lanes.
+    const bool open = act && (dd < 0.f);
+    const unsigned mo = __ballot_sync(0xffffffffu, open);
+    if (act && !open) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
+    if (mo) {
+      int nl = *(volatile int *)&wq.fill[1];
+      if (nl + __popc(mo) > HY_LCAP) { drain_long(0, nl); nl = 0; __syncwarp(); }   // rare: make room
+      if (open) {
+        const int l = nl + __popc(mo & lt_mask);
+        wq.le[l] = make_float4(tt * inv_fact[KFIX - 1 + HY_STAGE2],            // back to P(k)
+                               dd, fmaf(qq, (float)(KFIX - 1 + HY_STAGE2), aa), qq);
+        wq.lw[l] = w;
+      }
+      nl += __popc(mo);
+      __syncwarp();
+      if (nl >= 32) { nl -= 32; drain_long(nl, 32); }
+      if (lane == 0) wq.fill[1] = nl;
+      __syncwarp();
+    }
   };
   // one mixture step for up to 32 queued entries; rejected entries go back to the queue (returns
   // how many), so the warp never spins in a rejection loop
@@ -387,232 +431,213 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
     return __popc(m);
   };
 
-  // Work decomposition: a chunk is a strip of 32 gene quads (one per lane, 128 genes = 512
-  // contiguous bytes of each X row) times HY_CHUNK_CELLS consecutive cells.  The per-gene
-  // parameters are loaded once per chunk; per cell only the means float4 (coalesced across
-  // the warp) and the two per-cell scalars are read, one and two cells ahead of their use.
-  const uint32_t n_strips = (Q + 31u) / 32u;
-  // cells are visited in `cell_order` (grouped by tree row so that concurrently running warps
-  // share means rows in L2/L1); results do not depend on the order
-  auto load_means = [&](int32_t r, uint32_t g0) -> float4 {       // r validated in load_meta
-    if constexpr (VEC) {
-      return ldg_f4_hint(means + ((uint64_t)(uint32_t)r * G + g0), keep);
-    } else {
-      float m[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] = (g0 + j < G) ? means[(uint64_t)(uint32_t)r * G + g0 + j] : 1.f;
-      return make_float4(m[0], m[1], m[2], m[3]);
-    }
-  };
-
-  // chunks are handed out dynamically (g_sched[sched][0] is the next-chunk counter): warps whose
-  // queues drain more often simply take fewer chunks
   for (;;) {
     unsigned claimed = 0;
     if (lane == 0) claimed = atomicAdd(&g_sched[sched][0], 1u);
     claimed = __shfl_sync(0xffffffffu, claimed, 0);
-    if ((int64_t)claimed >= n_chunks) break;                  // no work left
-    const uint32_t cgroup = claimed / n_strips;
-    const uint32_t strip = claimed - cgroup * n_strips;
+    if ((uint64_t)claimed >= n_chunks) break;                 // no work left
+    const uint32_t grp = claimed / n_strips;
+    const uint32_t strip = claimed - grp * n_strips;
+    const uint4 gd = __ldg(groups + grp);                     // first position in `order`, cells, tree row
+    const uint32_t pos0 = gd.x;
+    const int n_cells = (int)gd.y;
     // lanes past the last quad of the last strip repeat quad Q-1: same key, same counts, same
     // addresses, so the duplicates are harmless and no per-count "lane is live" predicate is needed
     const uint32_t quad = min(strip * 32u + (uint32_t)lane, Q - 1u);
     const bool lane_first = strip * 32u + (uint32_t)lane < Q;     // not one of the repeated edge lanes
     const uint32_t g0 = quad * 4u;
-    const int64_t cell_lo = (int64_t)cgroup * HY_CHUNK_CELLS;
-    const int n_cells = (int)((n - cell_lo) < HY_CHUNK_CELLS ? (n - cell_lo) : HY_CHUNK_CELLS);
-    // per-gene parameters of this lane's quad, once per chunk
-    float al[4], bm[4];
-    if (VEC) {
-      const float4 av = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
-      const float4 bv = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
-      al[0] = av.x; al[1] = av.y; al[2] = av.z; al[3] = av.w;
-      bm[0] = bv.x; bm[1] = bv.y; bm[2] = bv.z; bm[3] = bv.w;
-    } else {
+    // per-(row, gene) constants of this lane's quad, once per chunk
+    float m[4], c[4], bm[4], smax[4];
+    {
+      float al[4];
+      const float *mrow = means + (uint64_t)gd.z * G + g0;
+      if (VEC) {
+        const float4 av = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
+        const float4 mv = ldg_f4_hint(mrow, keep);
+        al[0] = av.x; al[1] = av.y; al[2] = av.z; al[3] = av.w;
+        bm[0] = bv.x; bm[1] = bv.y; bm[2] = bv.z; bm[3] = bv.w;
+        m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = g0 + j < G;
+          al[j] = ok ? alpha[g0 + j] : 0.f;
+          bm[j] = ok ? beta_m1[g0 + j] : 1.f;
+          m[j] = ok ? mrow[j] : 1.f;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool ok = g0 + j < G;
-        al[j] = ok ? alpha[g0 + j] : 0.f;
-        bm[j] = ok ? beta_m1[g0 + j] : 1.f;
+        c[j] = al[j] * m[j];
+        smax[j] = ALL_MIX ? -1.f : nb_inversion_s_max(m[j], al[j], bm[j]);
       }
     }
-    // theta = alpha*mu + (beta-1) >= beta-1 when alpha, mu >= 0, so the Poisson-limit series below can
-    // only be needed in chunks where some gene has beta-1 < 0.1 (or a negative alpha): one vote per chunk
-    const float al_min = fminf(fminf(al[0], al[1]), fminf(al[2], al[3]));
-    const float bm_min = fminf(fminf(bm[0], bm[1]), fminf(bm[2], bm[3]));
-    const bool chunk_small_theta = __any_sync(0xffffffffu, bm_min < kSmallTheta || al_min < 0.f);
-    // gamma shape r = mu/theta <= 1/alpha when beta-1 >= 0: shapes above kInvShapeMax need a tiny alpha
-    const bool chunk_big_shape = __any_sync(0xffffffffu, !(al_min * kInvShapeMax >= 1.001f) || bm_min < 0.f);
-    // Per-cell metadata (cell id, tree row, library size) is the same for every lane: lane l
-    // loads it for cell (group*32 + l) with one coalesced request per 32 cells and the loop
-    // broadcasts it with shuffles.  The means quad of the next cell is prefetched: register load
-    // in the scalar path, cp.async into this lane's shared-memory slot in the vector path (a
-    // prefetch that survives the queue drains without occupying registers).
-    int32_t meta_cell = 0, meta_row = 0; float meta_s = 1.f;
-    auto load_meta = [&](int first) {                       // cells first .. first+31 of this chunk
+    // theta = c s + (beta-1) >= beta-1 on the inversion route, so the Poisson-limit series below can only
+    // be needed in chunks where some gene has beta-1 < 0.1: one vote per chunk
+    const bool chunk_small_theta =
+        __any_sync(0xffffffffu, fminf(fminf(bm[0], bm[1]), fminf(bm[2], bm[3])) < kSmallTheta);
+    // Per-cell metadata (cell id, library size) is the same for every lane: lane l loads it for cell
+    // (first + l) of the group with one coalesced request per 32 cells and the loop broadcasts it with
+    // shuffles.  A library size that is not positive and finite is flagged and sampled as NaN (every
+    // count of the cell goes to the mixture queue, whose drain leaves 0).
+    int32_t meta_cell = 0; float meta_s = 1.f;
+    auto load_meta = [&](int first) {                       // cells first .. first+31 of this group
       const int i = first + lane;
-      const int64_t pos = cell_lo + (i < n_cells ? i : n_cells - 1);
-      meta_cell = cell_order ? cell_order[pos] : (int32_t)pos;
-      meta_row = row_of_cell[meta_cell];
+      meta_cell = order[pos0 + (uint32_t)(i < n_cells ? i : n_cells - 1)];
       meta_s = scaling[meta_cell];
-      // rows are validated here, once per cell: a bad row is flagged (the caller raises) and
-      // sampled from row 0 so that every address below stays in range
-      if (!((uint32_t)meta_row < P)) { flag |= PST_FLAG_ROW; meta_row = 0; }
-    };
-    auto stage_means = [&](int32_t r) {
-      cp_async16(&wq.mstage[lane], means + ((uint64_t)(uint32_t)r * G + g0), keep);
-      cp_async_commit();
+      if (!(meta_s > 0.f && meta_s < 3.0e38f)) { flag |= PST_FLAG_DOMAIN; meta_s = __int_as_float(0x7fc00000); }
     };
     load_meta(0);
-    int32_t row = __shfl_sync(0xffffffffu, meta_row, 0);
-    float4 mcur = load_means(row, g0);
     for (int ci = 0; ci < n_cells; ++ci) {
       const int src = ci & 31;
       const int32_t cell = __shfl_sync(0xffffffffu, meta_cell, src);
       const float s = __shfl_sync(0xffffffffu, meta_s, src);
-      // next cell's tree row (clamped at the end of the chunk), then its means quad
       if (src == 31) load_meta(ci + 1);                     // warp-uniform branch, every 32 cells
-      const int32_t row1 = __shfl_sync(0xffffffffu, meta_row, (ci + 1 < n_cells) ? ((ci + 1) & 31) : src);
-      float4 mnext;
-      if (VEC) stage_means(row1);                           // lands during this iteration
-      else mnext = load_means(row1, g0);
 
       // ---- this cell's quad
-      const float m[4] = {mcur.x, mcur.y, mcur.z, mcur.w};
-      float t[4], d[4], a[4], q[4], mu[4], th[4], e2[4];
+      float t[4], d[4], a[4], q[4], mu[4], th[4];
       int cnt[4];
       bool small[4];
-      if constexpr (ALL_MIX) {
-        // "gamma_poisson" sampler: every count is drawn by the mixture (through the same queue)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mu[j] = m[j] * s;
-          th[j] = fmaf(al[j], mu[j], bm[j]);
-          small[j] = false; t[j] = 0.f; d[j] = 0.f; a[j] = 0.f; q[j] = 0.f; e2[j] = 0.f; cnt[j] = 0;
-        }
-      } else {
-      const int64_t gcell = cell0 + cell;
-      const uint4 rnd = philox(key, quad, (uint32_t)gcell,
-                               (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
-      float fw[4] = {(float)rnd.x, (float)rnd.y, (float)rnd.z, (float)rnd.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         mu[j] = m[j] * s;
-        th[j] = fmaf(al[j], mu[j], bm[j]);
-        nb_inversion_params_fast(mu[j], th[j], q[j], a[j], e2[j]);
-        // inversion only for small mean and variance (nb_route_inversion without the shape test)
-        small[j] = (mu[j] > 0.f) && (mu[j] <= mu_max) && (th[j] > 0.f) && (mu[j] * (1.0f + th[j]) <= var_max);
+        th[j] = fmaf(c[j], s, bm[j]);
+        small[j] = s <= smax[j];                    // the inversion's route (false on NaN)
       }
-      // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
-      if (chunk_small_theta && fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < kSmallTheta) {
+      if constexpr (ALL_MIX) {
+        // "gamma_poisson" sampler: every count is drawn by the mixture (through the same queue)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) e2[j] = (th[j] < kSmallTheta) ? nb_log2p0_small_theta(mu[j], th[j]) : e2[j];
-      }
-      // large gamma shapes (nearly Poisson genes with theta >= 0.1) go to the mixture: r log2(1+theta)
-      // would carry too large an error.  r <= 1/alpha, so only chunks with a tiny alpha can have them
-      if (chunk_big_shape) {
+        for (int j = 0; j < 4; ++j) { t[j] = 0.f; d[j] = 0.f; a[j] = 0.f; q[j] = 0.f; cnt[j] = 0; }
+      } else {
+        float e2[4];
+        const int64_t gcell = cell0 + cell;
+        const uint4 rnd = philox(key, quad, (uint32_t)gcell,
+                                 (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 0u);
+        float fw[4] = {(float)rnd.x, (float)rnd.y, (float)rnd.z, (float)rnd.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) small[j] = small[j] && nb_shape_ok(th[j], q[j], a[j]);
-      }
-      // The top 2^-14 of the uniforms is not decided in fp32: those counts (chosen by the Philox word
-      // alone) are appended with their parameters to the launch's tail list and inverted in fp64 by
-      // tail_fix_kernel; the head sees them as decided (their word is replaced by one that gives
-      // cdf(0) - u > 0: count 0 until the fix-up writes it)
-      if (fmaxf(fmaxf(fw[0], fw[1]), fmaxf(fw[2], fw[3])) >= kTailWord) {
+        for (int j = 0; j < 4; ++j) nb_inversion_params_fast(mu[j], th[j], q[j], a[j], e2[j]);
+        // theta -> 0 (Poisson limit): log1p(theta)/theta by series, exact as theta -> 0
+        if (chunk_small_theta && fminf(fminf(th[0], th[1]), fminf(th[2], th[3])) < kSmallTheta) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (small[j] && (fw[j] >= kTailWord) && (VEC || g0 + j < G)) {
-            if (lane_first) {                          // repeated edge lanes leave the listing to their twin
-              const unsigned slot = atomicAdd(tail, 1u);
-              if (slot < tail_cap)
-                reinterpret_cast<uint4 *>(tail + 4)[slot] =
-                    make_uint4((uint32_t)cell, g0 + j, __float_as_uint(mu[j]), __float_as_uint(th[j]));
-              else
-                flag |= PST_FLAG_SCRATCH;
+          for (int j = 0; j < 4; ++j) e2[j] = (th[j] < kSmallTheta) ? nb_log2p0_small_theta(mu[j], th[j]) : e2[j];
+        }
+        // The top 2^-14 of the uniforms is not decided in fp32: those counts (chosen by the Philox word
+        // alone) are appended with their parameters to the launch's tail list and finished by
+        // tail_fix_kernel; the head sees them as decided (their word is replaced by one that gives
+        // cdf(0) - u > 0: count 0 until the fix-up writes it)
+        if (fmaxf(fmaxf(fw[0], fw[1]), fmaxf(fw[2], fw[3])) >= kTailWord) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (small[j] && (fw[j] >= kTailWord) && (VEC || g0 + j < G)) {
+              if (lane_first) {                          // repeated edge lanes leave the listing to their twin
+                const unsigned slot = atomicAdd(tail, 1u);
+                if (slot < tail_cap)
+                  reinterpret_cast<uint4 *>(tail + 4)[slot] =
+                      make_uint4((uint32_t)cell, g0 + j, __float_as_uint(mu[j]), __float_as_uint(th[j]));
+                else
+                  flag |= PST_FLAG_SCRATCH;
+              }
+              fw[j] = -4.0e9f;
             }
-            fw[j] = -4.0e9f;
           }
         }
-      }
-      // P(0) and cdf(0) - u for the inversion lanes
+        // P(0) and cdf(0) - u for the inversion lanes
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[j] = ex2_fast(e2[j]);                     // P(0)
-        d[j] = cdf0_minus_u(t[j], fw[j]);           // cdf(0) - u, one FFMA
-        cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
+        for (int j = 0; j < 4; ++j) {
+          t[j] = ex2_fast(e2[j]);                     // P(0)
+          d[j] = cdf0_minus_u(t[j], fw[j]);           // cdf(0) - u, one FFMA
+          cnt[j] = (int)(__float_as_uint(d[j]) >> 31);
+        }
       }
-      }  // !ALL_MIX
       // large means: queue them for the mixture now, so mu/theta are dead during the head.  Many
-      // (cell, strip) pairs have none: one vote skips the four ballots
+      // (cell, strip) pairs have none: one vote skips the block
       if (ALL_MIX || __any_sync(0xffffffffu, !(small[0] && small[1] && small[2] && small[3]))) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool to_mix = !small[j] && (VEC || g0 + j < G);
-        const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
-        if (to_mix) {
-          const int e = ng + __popc(mg & lt_mask);
-          wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
-          wq.ga[e] = 0;
+        for (int j = 0; j < 4; ++j) {
+          const bool to_mix = !small[j] && (VEC || g0 + j < G);
+          const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
+          if (to_mix) {
+            const int e = ng + __popc(mg & lt_mask);
+            wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
+            wq.ga[e] = 0;
+          }
+          ng += __popc(mg);
         }
-        ng += __popc(mg);
-      }
       }
       // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
       if constexpr (!ALL_MIX) {
 #pragma unroll
-      for (int k = 0; k < KFIX - 1; ++k) {
+        for (int k = 0; k < KFIX - 1; ++k) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          t[j] = inv_t_next(t[j], a[j], q[j], k);                // t_{k+1} = P(k+1) (k+1)!
-          d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
-          cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
+          for (int j = 0; j < 4; ++j) {
+            t[j] = inv_t_next(t[j], a[j], q[j], k);                // t_{k+1} = P(k+1) (k+1)!
+            d[j] = fmaf(t[j], inv_fact[k + 1], d[j]);              // cdf(k+1) - u
+            cnt[j] += (int)(__float_as_uint(d[j]) >> 31);
+          }
         }
-      }
-      }  // !ALL_MIX
-      bool to_search[4];
-      int out[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        to_search[j] = (VEC || g0 + j < G) && small[j] && (d[j] < 0.f);
-        out[j] = cnt[j];
       }
       // store the quad: undecided and mixture slots hold a partial count until their queue entry is
       // drained, which always writes them (the __syncwarp below orders this store before the drain's)
       {
         int32_t *dst = X + ((uint64_t)(uint32_t)cell * ldx + g0);
         if (VEC) {
-          *reinterpret_cast<int4 *>(dst) = make_int4(out[0], out[1], out[2], out[3]);
+          *reinterpret_cast<int4 *>(dst) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (g0 + j < G) dst[j] = out[j];
+            if (g0 + j < G) dst[j] = cnt[j];
         }
       }
-      // enqueue the undecided inversions (all lanes take part in the ballots)
+      // enqueue the undecided inversions
+      if constexpr (!ALL_MIX) {
+#if HY_ENQ_ATOMIC
+        // slots come from a shared-memory counter
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned ms = __ballot_sync(0xffffffffu, to_search[j]);
-        if (to_search[j]) {
-          const int e = ns + __popc(ms & lt_mask);
-          wq.se[e] = make_float4(t[j], d[j], a[j], q[j]);     // t = P(KFIX-1) (KFIX-1)!, rescaled in the drain
-          wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
+        for (int j = 0; j < 4; ++j) {
+          if ((VEC || g0 + j < G) && small[j] && (d[j] < 0.f)) {
+            const int e = atomicAdd(&wq.fill[0], 1);
+            wq.se[e] = make_float4(t[j], d[j], a[j], q[j]);     // t = P(KFIX-1) (KFIX-1)!, rescaled in the drain
+            wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
+          }
         }
-        ns += __popc(ms);
+        __syncwarp();
+        ns = *(volatile int *)&wq.fill[0];
+#else
+        // slots from ballots (all lanes take part)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool push = (VEC || g0 + j < G) && small[j] && (d[j] < 0.f);
+          const unsigned ms = __ballot_sync(0xffffffffu, push);
+          if (push) {
+            const int e = ns + __popc(ms & lt_mask);
+            wq.se[e] = make_float4(t[j], d[j], a[j], q[j]);     // t = P(KFIX-1) (KFIX-1)!, rescaled in the drain
+            wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
+          }
+          ns += __popc(ms);
+        }
+        __syncwarp();
+#endif
+      } else {
+        __syncwarp();
       }
-      __syncwarp();
-      while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
-      while (ng >= 32) { ng -= 32; ng += drain_mixture(ng, 32); }
-      __syncwarp();
-      // rotate the pipeline
-      if (VEC) {
-        cp_async_wait_all();                       // this lane's slot for cell ci+1 has landed
-        mnext = wq.mstage[lane];
+      if (ns >= 32 || ng >= 32) {
+        while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
+        while (ng >= 32) { ng -= 32; ng += drain_mixture(ng, 32); }
+#if HY_ENQ_ATOMIC
+        if (lane == 0) wq.fill[0] = ns;
+#endif
+        __syncwarp();
       }
-      row = row1; mcur = mnext;
     }
   }
   if (ns > 0) drain_search(0, ns);
-  while (ng > 0) { const int c = ng < 32 ? ng : 32; ng -= c; ng += drain_mixture(ng, c); }
+  __syncwarp();
+  {
+    const int nl = *(volatile int *)&wq.fill[1];
+    if (nl > 0) drain_long(0, nl);
+  }
+  while (ng > 0) { const int cdone = ng < 32 ? ng : 32; ng -= cdone; ng += drain_mixture(ng, cdone); }
   if (flag) atomicOr(flags, flag);
   // the last warp to leave rearms the scheduler words for the next launch
   if (lane == 0) {
@@ -622,23 +647,27 @@ draw_counts_hybrid_kernel(const __grid_constant__ PhiloxKey key, const float *__
 }
 
 // Parity hook: the fp32 parameterisation exactly as the draw kernel computes it (same __device__
-// functions), one element per (mu, alpha, beta-1) triple.
-__global__ void nb_params_f32_kernel(const float *__restrict__ mu, const float *__restrict__ alpha,
-                                     const float *__restrict__ beta_m1, int64_t n, float *__restrict__ out_theta,
+// functions, same operation order), one element per (M, s, alpha, beta-1).
+__global__ void nb_params_f32_kernel(const float *__restrict__ M, const float *__restrict__ scaling,
+                                     const float *__restrict__ alpha, const float *__restrict__ beta_m1, int64_t n,
+                                     float *__restrict__ out_mu, float *__restrict__ out_theta,
                                      float *__restrict__ out_r, float *__restrict__ out_q, float *__restrict__ out_a,
                                      float *__restrict__ out_log2p0, int32_t *__restrict__ out_route) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float m = mu[i];
-    const float th = fmaf(alpha[i], m, beta_m1[i]);
+    const float m = M[i], s = scaling[i];
+    const float mu = m * s;
+    const float th = fmaf(alpha[i] * m, s, beta_m1[i]);
     float q, a, e2;
-    nb_inversion_params(m, th, q, a, e2);
+    nb_inversion_params(mu, th, q, a, e2);
+    out_mu[i] = mu;
     out_theta[i] = th;
-    out_r[i] = nb_shape(m, th);
+    out_r[i] = nb_shape(mu, th);
     out_q[i] = q;
     out_a[i] = a;
     out_log2p0[i] = e2;
-    out_route[i] = !nb_domain_ok(m, th) ? PST_ROUTE_DOMAIN_ERROR
-                   : nb_route_inversion(m, th, q, a) ? PST_ROUTE_INVERSION : PST_ROUTE_MIXTURE;
+    const bool s_ok = s > 0.f && s < 3.0e38f;
+    const bool inv = s_ok && (s <= nb_inversion_s_max(m, alpha[i], beta_m1[i]));
+    out_route[i] = inv ? PST_ROUTE_INVERSION : (s_ok && nb_domain_ok(mu, th)) ? PST_ROUTE_MIXTURE : PST_ROUTE_DOMAIN_ERROR;
   }
 }
 
@@ -655,35 +684,68 @@ __global__ void tail_fix_kernel(const __grid_constant__ PhiloxKey key, const uin
 }
 
 // ---------------------------------------------------------------------------
-// cells grouped by tree row (counting sort): order[] lists the cells of row 0, then row 1, ...
+// Cells grouped by tree row (counting sort) and cut into groups of at most HY_CHUNK_CELLS cells of one
+// row: order[] lists the cells of row 0, then row 1, ...; groups[g] = (first position in order, cells,
+// row, 0).  Four small kernels in front of every draw; the layout never changes the counts.
 // ---------------------------------------------------------------------------
 __global__ void row_histogram_kernel(const int32_t *__restrict__ row_of_cell, int64_t n, int32_t P,
-                                     uint32_t *__restrict__ bins) {
+                                     uint32_t *__restrict__ bins, uint32_t *__restrict__ flags) {
+  bool bad = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t r = row_of_cell[i];
-    atomicAdd(&bins[(uint32_t)r < (uint32_t)P ? r : 0], 1u);
+    const bool ok = (uint32_t)r < (uint32_t)P;
+    bad |= !ok;                                            // flagged (the caller raises), sampled from row 0
+    atomicAdd(&bins[ok ? r : 0], 1u);
   }
+  if (bad) atomicOr(flags, PST_FLAG_ROW);
 }
 
-__global__ void row_scan_kernel(uint32_t *bins, int32_t P) {      // exclusive scan, one CTA
-  __shared__ uint32_t part[1024];
+// exclusive scans over the rows, one CTA: bins[r] -> first position of row r (bins[P] = n),
+// gstart[r] -> first group of row r (gstart[P] = number of groups, also written to hdr[1])
+__global__ void row_scan_kernel(uint32_t *bins, uint32_t *gstart, int32_t P, uint32_t *hdr) {
+  __shared__ uint32_t part[1024], gpart[1024];
   const int t = threadIdx.x;
   const int per = (P + 1023) / 1024;
-  const int lo = t * per, hi = min(P, lo + per);
-  uint32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += bins[i];
+  const int lo = min(P, t * per), hi = min(P, lo + per);
+  uint32_t sum = 0, gsum = 0;
+  for (int i = lo; i < hi; ++i) { const uint32_t cnt = bins[i]; sum += cnt; gsum += (cnt + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS; }
   part[t] = sum;
+  gpart[t] = gsum;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {
-    const uint32_t v = t >= off ? part[t - off] : 0u;
+    const uint32_t v = t >= off ? part[t - off] : 0u, gv = t >= off ? gpart[t - off] : 0u;
     __syncthreads();
     part[t] += v;
+    gpart[t] += gv;
     __syncthreads();
   }
-  uint32_t run = part[t] - sum;
-  for (int i = lo; i < hi; ++i) { const uint32_t c = bins[i]; bins[i] = run; run += c; }
+  uint32_t run = part[t] - sum, grun = gpart[t] - gsum;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t cnt = bins[i];
+    bins[i] = run;
+    gstart[i] = grun;
+    run += cnt;
+    grun += (cnt + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS;
+  }
+  if (t == 1023) { bins[P] = part[1023]; gstart[P] = gpart[1023]; hdr[1] = gpart[1023]; }
 }
 
+__global__ void group_table_kernel(const uint32_t *__restrict__ bins, const uint32_t *__restrict__ gstart, int32_t P,
+                                   uint4 *__restrict__ groups) {
+  const uint32_t ng = gstart[P];
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += gridDim.x * blockDim.x) {
+    int lo = 0, hi = P;                                    // last row r with gstart[r] <= g
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (gstart[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint32_t piece = g - gstart[lo];
+    const uint32_t pos0 = bins[lo] + piece * HY_CHUNK_CELLS;
+    groups[g] = make_uint4(pos0, min((uint32_t)HY_CHUNK_CELLS, bins[lo + 1] - pos0), (uint32_t)lo, 0u);
+  }
+}
+
+// runs AFTER group_table_kernel: the scatter advances bins[r] from the first to the last position of row r
 __global__ void row_scatter_kernel(const int32_t *__restrict__ row_of_cell, int64_t n, int32_t P,
                                    uint32_t *__restrict__ bins, int32_t *__restrict__ order) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -830,54 +892,57 @@ extern "C" int pst_count_stats(const int32_t *X, int64_t n, int64_t G, int64_t l
 }
 
 
-extern "C" int pst_group_cells_by_row(const int32_t *row_of_cell, int64_t n, int32_t P,
-                                      uint32_t *bins, int32_t *order, void *stream) {
-  const char *fn = "pst_group_cells_by_row";
-  PST_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && P > 0, fn, "need 0 <= n < 2^31 and P > 0");
-  if (n == 0) return 0;
-  PST_REQUIRE(row_of_cell && bins && order, fn, "null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(bins, 0, sizeof(uint32_t) * (size_t)P, st);
-  if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "memset failed"); }
-  const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sm() * 8);
-  row_histogram_kernel<<<g, 256, 0, st>>>(row_of_cell, n, P, bins);
-  int rc = check_launch(fn);
-  if (rc) return rc;
-  row_scan_kernel<<<1, 1024, 0, st>>>(bins, P);
-  rc = check_launch(fn);
-  if (rc) return rc;
-  row_scatter_kernel<<<g, 256, 0, st>>>(row_of_cell, n, P, bins, order);
-  return check_launch(fn);
-}
-
-
-extern "C" int pst_nb_params_f32(const float *mu, const float *alpha, const float *beta_m1, int64_t n,
-                                 float *out_theta, float *out_r, float *out_q, float *out_a, float *out_log2p0,
-                                 int32_t *out_route, void *stream) {
+extern "C" int pst_nb_params_f32(const float *M, const float *scaling, const float *alpha, const float *beta_m1,
+                                 int64_t n, float *out_mu, float *out_theta, float *out_r, float *out_q, float *out_a,
+                                 float *out_log2p0, int32_t *out_route, void *stream) {
   const char *fn = "pst_nb_params_f32";
   PST_REQUIRE(n >= 0, fn, "negative size");
   if (n == 0) return 0;
-  PST_REQUIRE(mu && alpha && beta_m1 && out_theta && out_r && out_q && out_a && out_log2p0 && out_route, fn,
-              "null pointer");
+  PST_REQUIRE(M && scaling && alpha && beta_m1 && out_mu && out_theta && out_r && out_q && out_a && out_log2p0 &&
+              out_route, fn, "null pointer");
   const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sm() * 8);
-  nb_params_f32_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(mu, alpha, beta_m1, n, out_theta, out_r, out_q, out_a,
-                                                            out_log2p0, out_route);
+  nb_params_f32_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(M, scaling, alpha, beta_m1, n, out_mu, out_theta, out_r,
+                                                            out_q, out_a, out_log2p0, out_route);
   return check_launch(fn);
 }
 
-extern "C" int64_t pst_draw_scratch_words(int64_t n, int64_t G) {
-  if (n <= 0 || G <= 0) return 4;
-  // 4 header words + 4 words per listed count; twice the expected 2^-14 n G entries plus 1024: a list
-  // that does not fit would be a > 30 sigma event
+// scratch layout of pst_draw_counts (uint32 words): [0] tail entries appended, [1] number of groups,
+// [2..3] unused | tail list, 4 words per entry | order[n] | bins[P+1] | gstart[P+1] | groups, 4 words each
+namespace {
+struct DrawLayout { int64_t tail_cap, order, bins, gstart, groups, max_groups, words; };
+DrawLayout draw_layout(int64_t n, int64_t G, int64_t P) {
+  DrawLayout L;
+  // twice the expected 2^-14 n G listed counts plus 1024: a list that does not fit would be a > 30 sigma event
   const double expect = (double)n * (double)G / 16384.0;
-  return 4 + 4 * ((int64_t)(2.0 * expect) + 1024);
+  L.tail_cap = std::min<int64_t>((int64_t)(2.0 * expect) + 1024, (int64_t)0xfffffff0);
+  L.order = 4 + 4 * L.tail_cap;
+  L.bins = L.order + n;
+  L.gstart = L.bins + P + 1;
+  L.groups = (L.gstart + P + 1 + 3) & ~(int64_t)3;          // uint4 entries: 16-byte aligned
+  L.max_groups = n / HY_CHUNK_CELLS + P + 1;
+  L.words = L.groups + 4 * L.max_groups;
+  return L;
+}
+}  // namespace
+
+extern "C" int64_t pst_draw_scratch_words(int64_t n, int64_t G, int64_t P) {
+  if (n <= 0 || G <= 0 || P <= 0) return 4;
+  return draw_layout(n, G, P).words;
+}
+
+extern "C" int pst_draw_scratch_layout(int64_t n, int64_t G, int64_t P, int64_t *h_out) {
+  if (n <= 0 || G <= 0 || P <= 0 || !h_out) return -1;
+  const DrawLayout L = draw_layout(n, G, P);
+  h_out[0] = L.tail_cap; h_out[1] = L.order; h_out[2] = L.bins; h_out[3] = L.gstart; h_out[4] = L.groups;
+  h_out[5] = L.max_groups;
+  return 0;
 }
 
 extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const int32_t *row_of_cell,
                                const float *scaling, const float *alpha, const float *beta_m1,
                                uint64_t seed, int64_t cell0, int64_t n, int32_t *X, int64_t ldx,
-                               uint32_t *flags, int32_t sampler, const int32_t *cell_order,
-                               uint32_t *scratch, int64_t scratch_words, void *stream) {
+                               uint32_t *flags, int32_t sampler, uint32_t *scratch, int64_t scratch_words,
+                               void *stream) {
   const char *fn = "pst_draw_counts";
   PST_REQUIRE(P >= 0 && G >= 0 && n >= 0 && cell0 >= 0, fn, "negative size");
   PST_REQUIRE(ldx >= G, fn, "ldx < G");
@@ -887,73 +952,68 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   PST_REQUIRE(cell0 + n < (int64_t)1 << 48, fn, "cell index must be below 2^48");
   PST_REQUIRE(sampler == PST_SAMPLER_GAMMA_POISSON || sampler == PST_SAMPLER_HYBRID, fn, "unknown sampler");
   if (n == 0 || G == 0) return 0;
+  PST_REQUIRE(P > 0, fn, "the means table has no rows");
   PST_REQUIRE(means && row_of_cell && scaling && alpha && beta_m1 && X && flags, fn, "null pointer");
+  const DrawLayout L = draw_layout(n, G, P);
+  PST_REQUIRE(scratch && scratch_words >= L.words, fn, "scratch must hold pst_draw_scratch_words(n, G, P) words");
+  PST_REQUIRE((uintptr_t)scratch % 16 == 0, fn, "scratch must be 16-byte aligned");
   const int64_t Q = (G + 3) / 4;
   const bool vec = (G % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)means % 16 == 0) &&
                    ((uintptr_t)alpha % 16 == 0) && ((uintptr_t)beta_m1 % 16 == 0) &&
                    ((uintptr_t)X % 16 == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  {
-    // The route thresholds and the head length are part of the sampler's definition (they decide
-    // which uniforms a count consumes).  A developer build (-DPST_DEV_KNOBS, tools/tune_hybrid.sh)
-    // can override them from the environment for profiling sweeps; the product build cannot.
-#ifdef PST_DEV_KNOBS
-    static const int kfix = getenv("PST_HY_KFIX") ? atoi(getenv("PST_HY_KFIX")) : HY_KFIX;
-    static const float mu_max = getenv("PST_HY_MU_MAX") ? (float)atof(getenv("PST_HY_MU_MAX")) : HY_MU_MAX;
-    static const float var_max = getenv("PST_HY_VAR_MAX") ? (float)atof(getenv("PST_HY_VAR_MAX")) : HY_VAR_MAX;
-    static const int ctas_per_sm = getenv("PST_HY_CTAS") ? atoi(getenv("PST_HY_CTAS")) : HY_MIN_CTAS;
-#else
-    const int kfix = HY_KFIX;
-    const float mu_max = HY_MU_MAX, var_max = HY_VAR_MAX;
-    const int ctas_per_sm = HY_MIN_CTAS;
-#endif
-    const int64_t n_chunks = ((n + HY_CHUNK_CELLS - 1) / HY_CHUNK_CELLS) * ((Q + 31) / 32);
-    PST_REQUIRE(n_chunks < ((int64_t)1 << 31), fn, "too many work chunks in one call (chunk the cells)");
-    const int64_t need = (n_chunks + HY_WARPS - 1) / HY_WARPS;
-    const int64_t cap = (int64_t)num_sm() * ctas_per_sm;    // persistent CTAs of 4 warps, one wave
-    const int slot = sched_slot(stream);
-    PST_REQUIRE(slot >= 0, fn, "more than 4096 distinct streams have called pst_draw_counts on this device");
-    // tail list of the hybrid sampler: scratch[0] = entries appended, entries from word 4 on
-    uint32_t tail_cap = 0;
-    if (sampler == PST_SAMPLER_HYBRID) {
-      PST_REQUIRE(scratch && scratch_words >= pst_draw_scratch_words(n, G), fn,
-                  "the hybrid sampler needs pst_draw_scratch_words(n, G) words of scratch");
-      PST_REQUIRE((uintptr_t)scratch % 16 == 0, fn, "scratch must be 16-byte aligned");
-      tail_cap = (uint32_t)std::min<int64_t>((scratch_words - 4) / 4, (int64_t)0xffffffff);
-      const cudaError_t e = cudaMemsetAsync(scratch, 0, 16, st);
-      if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "memset failed"); }
-    }
-    const unsigned hb = (unsigned)(need < cap ? need : cap);
-#define PST_LAUNCH_HYBRID(KF, MIX)                                                                         \
-    do {                                                                                                   \
-      if (vec) draw_counts_hybrid_kernel<KF, true, MIX><<<hb, HY_THREADS, 0, st>>>(                        \
-          PhiloxKey(seed), means, (uint32_t)P, (uint32_t)G, (uint32_t)Q, row_of_cell, scaling, alpha,      \
-          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max, slot, scratch, tail_cap);                  \
-      else draw_counts_hybrid_kernel<KF, false, MIX><<<hb, HY_THREADS, 0, st>>>(                           \
-          PhiloxKey(seed), means, (uint32_t)P, (uint32_t)G, (uint32_t)Q, row_of_cell, scaling, alpha,      \
-          beta_m1, cell0, n, X, (uint32_t)ldx, flags, cell_order, mu_max, var_max, slot, scratch, tail_cap);                  \
-    } while (0)
-    if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
-      PST_LAUNCH_HYBRID(HY_KFIX, true);
-      return check_launch(fn);
-    }
-#ifdef PST_DEV_KNOBS
-    switch (kfix) {
-      case 6: PST_LAUNCH_HYBRID(6, false); break;
-      case 8: PST_LAUNCH_HYBRID(8, false); break;
-      default: PST_LAUNCH_HYBRID(HY_KFIX, false); break;
-    }
-#else
-    (void)kfix;
-    PST_LAUNCH_HYBRID(HY_KFIX, false);
-#endif
-#undef PST_LAUNCH_HYBRID
-    const int rc = check_launch(fn);
-    if (rc) return rc;
-    // expected entries: 2^-14 of the inverted counts; one thread each, grid-stride beyond that
-    const int64_t expect = (int64_t)((double)n * (double)G / 16384.0) + 256;
-    const unsigned tb = (unsigned)std::min<int64_t>((expect + 127) / 128, (int64_t)num_sm() * 16);
-    tail_fix_kernel<<<tb, 128, 0, st>>>(PhiloxKey(seed), scratch, tail_cap, cell0, X, (uint32_t)ldx);
+  const int64_t n_strips = (Q + 31) / 32;
+  PST_REQUIRE(L.max_groups * n_strips < ((int64_t)1 << 32) - 65536, fn, "too many work chunks in one call (chunk the cells)");
+  const int slot = sched_slot(stream);
+  PST_REQUIRE(slot >= 0, fn, "more than 4096 distinct streams have called pst_draw_counts on this device");
+
+  // ---- cells grouped by tree row, cut into groups of one row
+  uint32_t *bins = scratch + L.bins, *gstart = scratch + L.gstart;
+  int32_t *order = reinterpret_cast<int32_t *>(scratch + L.order);
+  uint4 *groups = reinterpret_cast<uint4 *>(scratch + L.groups);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 16, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(bins, 0, sizeof(uint32_t) * (size_t)(P + 1), st);
+  if (e != cudaSuccess) { cudaGetLastError(); return pst::fail_arg(fn, "memset failed"); }
+  const unsigned gg = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sm() * 8);
+  row_histogram_kernel<<<gg, 256, 0, st>>>(row_of_cell, n, (int32_t)P, bins, flags);
+  int rc = check_launch(fn);
+  if (rc) return rc;
+  row_scan_kernel<<<1, 1024, 0, st>>>(bins, gstart, (int32_t)P, scratch);
+  rc = check_launch(fn);
+  if (rc) return rc;
+  const unsigned gt = (unsigned)std::min<int64_t>((L.max_groups + 255) / 256, (int64_t)num_sm() * 8);
+  group_table_kernel<<<gt, 256, 0, st>>>(bins, gstart, (int32_t)P, groups);
+  rc = check_launch(fn);
+  if (rc) return rc;
+  row_scatter_kernel<<<gg, 256, 0, st>>>(row_of_cell, n, (int32_t)P, bins, order);
+  rc = check_launch(fn);
+  if (rc) return rc;
+
+  // ---- the draw: persistent CTAs of 4 warps, one wave; never more warps than chunks can exist
+  const int64_t need = (L.max_groups * n_strips + HY_WARPS - 1) / HY_WARPS;
+  const int64_t cap = (int64_t)num_sm() * HY_MIN_CTAS;
+  const unsigned hb = (unsigned)(need < cap ? need : cap);
+  const uint32_t tail_cap = (uint32_t)L.tail_cap;
+#define PST_LAUNCH_DRAW(MIX)                                                                                        \
+  do {                                                                                                              \
+    if (vec) draw_counts_kernel<HY_KFIX, true, MIX><<<hb, HY_THREADS, 0, st>>>(                                     \
+        PhiloxKey(seed), means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags,  \
+        scratch, order, groups, slot, scratch, tail_cap);                                                           \
+    else draw_counts_kernel<HY_KFIX, false, MIX><<<hb, HY_THREADS, 0, st>>>(                                        \
+        PhiloxKey(seed), means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags,  \
+        scratch, order, groups, slot, scratch, tail_cap);                                                           \
+  } while (0)
+  if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
+    PST_LAUNCH_DRAW(true);
     return check_launch(fn);
   }
+  PST_LAUNCH_DRAW(false);
+#undef PST_LAUNCH_DRAW
+  rc = check_launch(fn);
+  if (rc) return rc;
+  // the listed counts (2^-14 of the inverted ones): one thread each, grid-stride beyond the expectation
+  const int64_t expect = (int64_t)((double)n * (double)G / 16384.0) + 256;
+  const unsigned tb = (unsigned)std::min<int64_t>((expect + 127) / 128, (int64_t)num_sm() * 16);
+  tail_fix_kernel<<<tb, 128, 0, st>>>(PhiloxKey(seed), scratch, tail_cap, cell0, X, (uint32_t)ldx);
+  return check_launch(fn);
 }

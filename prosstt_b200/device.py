@@ -224,8 +224,7 @@ class CountEngine(object):
         self.alpha, self.beta_m1 = gene_params(alpha, beta, self.G, dev)
         self.sampler = nat.SAMPLERS[sampler]
         self.flags = torch.zeros(4, dtype=torch.int32, device=dev)   # status word (+3 reserved)
-        self.group_rows = not os.environ.get("PST_NO_GROUP")    # developer switch
-        self._order = self._bins = self._scratch = None
+        self._scratch = None
         self.overflow = None                                    # filled by draw_to_host (uint16 format)
 
     def draw(self, rows, scaling32, seed, cell0, out=None):
@@ -235,30 +234,19 @@ class CountEngine(object):
         if out is None:
             out = torch.empty((n, self.G), dtype=torch.int32, device=self.dev)
         st = nat.stream_ptr(self.dev)
-        order = None
         timers = CountEngine.timers
         if timers is not None:
             t0 = torch.cuda.Event(enable_timing=True)
             t0.record(torch.cuda.current_stream(self.dev))
-        if self.group_rows and n >= 2048 and self.sampler == nat.SAMPLER_HYBRID:
-            # visit the cells grouped by tree row: concurrently running warps then share means rows
-            if self._order is None or self._order.numel() < n:
-                self._order = torch.empty(n, dtype=torch.int32, device=self.dev)
-                self._bins = torch.empty(max(1, self.P), dtype=torch.int32, device=self.dev)
-            order = self._order[:n]
-            nat.call("pst_group_cells_by_row", nat.ptr(rows), n, self.P, nat.ptr(self._bins),
-                     nat.ptr(order), st)
-        scratch, words = None, 0
-        if self.sampler == nat.SAMPLER_HYBRID:
-            # list of the counts that the fix-up kernel inverts in fp64 (top 2^-14 of the uniforms)
-            words = int(nat.load().pst_draw_scratch_words(n, self.G))
-            if self._scratch is None or self._scratch.numel() < words:
-                self._scratch = torch.empty(words, dtype=torch.int32, device=self.dev)
-            scratch = self._scratch
+        # scratch of the call: visiting order of the cells (grouped by tree row) and the list of the counts
+        # that the fix-up kernel finishes with a 64-bit uniform (top 2^-14 of the uniforms)
+        words = int(nat.load().pst_draw_scratch_words(n, self.G, self.P))
+        if self._scratch is None or self._scratch.numel() < words:
+            self._scratch = torch.empty(words, dtype=torch.int32, device=self.dev)
         nat.call("pst_draw_counts", nat.ptr(self.means), self.P, self.G, nat.ptr(rows),
                  nat.ptr(scaling32), nat.ptr(self.alpha), nat.ptr(self.beta_m1),
                  seed, int(cell0), n, out.data_ptr(), out.stride(0) if n else self.G,
-                 nat.ptr(self.flags), self.sampler, order, scratch, words, st)
+                 nat.ptr(self.flags), self.sampler, self._scratch, words, st)
         if timers is not None:
             t1 = torch.cuda.Event(enable_timing=True)
             t1.record(torch.cuda.current_stream(self.dev))

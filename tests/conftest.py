@@ -42,3 +42,19 @@ def golden_lineage(name):
 def has_cuda():
     import torch
     return torch.cuda.is_available()
+
+
+def writer_inputs():
+    """Deterministic inputs of the text writers: tests/golden/make_golden.py feeds them to the reference's
+    writers (written_files.json), tests/test_host_maps.py to ours."""
+    rng = np.random.RandomState(17)
+    X = rng.negative_binomial(0.8, 0.2, size=(6, 5))
+    uMs = {"A": rng.normal(size=(3, 5)), "B": rng.normal(size=(2, 5)) * 1e-7}
+    H = rng.gamma(0.05, size=(2, 5))
+    labs = np.array([0, 1, 2, 3, 3, 4])
+    brns = np.array(["A", "A", "A", "B", "B", "B"])
+    scal = np.exp(rng.normal(0, 0.7, size=6))
+    gscale = np.exp(rng.normal(0.8, 1.0, size=5))
+    alpha = np.exp(rng.normal(np.log(0.2), np.log(1.5), size=5))
+    beta = np.exp(rng.normal(np.log(2.0), np.log(1.5), size=5)) + 1
+    return X, uMs, H, labs, brns, scal, gscale, alpha, beta

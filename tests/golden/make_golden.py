@@ -292,8 +292,32 @@ def gen_nbparams():
     print("nbparams.npz")
 
 
+def gen_written_files():
+    """Files written by the reference's own writers (tree_utils.py:59-173): the byte-level pin of the
+    on-disk formats."""
+    import tempfile
+    from prosstt import tree_utils as rtu
+    sys.path.insert(0, os.path.dirname(HERE))
+    from conftest import writer_inputs
+    X, uMs, H, labs, brns, scal, gscale, alpha, beta = writer_inputs()
+    t = rtree.Tree(topology=[["A", "B"]], time={"A": 3, "B": 2}, num_branches=2, branch_points=0, modules=2, G=5)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        rtu.save_matrices("job", tmp, X, uMs, H)
+        rtu.save_cell_params("job", tmp, labs, brns, scal)
+        rtu.save_gene_params("job", tmp, gscale, alpha, beta)
+        rtu.save_params("job", tmp, t, 7)
+        for name in sorted(os.listdir(tmp)):
+            with open(os.path.join(tmp, name)) as fh:
+                out[name] = fh.read()
+    with open(os.path.join(HERE, "written_files.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print("written_files.json", sorted(out))
+
+
 if __name__ == "__main__":
     gen_maps()
+    gen_written_files()
     cases = {c["name"]: c for c in tree_cases()}
     small = dict(name="abc", topology=[["A", "B"], ["A", "C"]],
                  time={"A": 9, "B": 12, "C": 7}, branch_points=1)

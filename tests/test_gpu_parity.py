@@ -9,6 +9,8 @@ Bars (BASELINE.json north_star):
     two-sample test against numpy's legacy negative_binomial on the same parameters);
   * counts bit-exact across cell partitions.
 """
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -699,12 +701,12 @@ def test_padded_row_stride_and_raw_abi_call():
     dense = eng.draw(rows, sc, 99, 5)
     padded = torch.full((n, ldx), -7, dtype=torch.int32, device=dev)
     status = torch.zeros(4, dtype=torch.int32, device=dev)
-    words = int(nat.load().pst_draw_scratch_words(n, G))
+    words = int(nat.load().pst_draw_scratch_words(n, G, tb.P))
     scratch = torch.empty(words, dtype=torch.int32, device=dev)
     for sampler in (nat.SAMPLER_HYBRID, nat.SAMPLER_GAMMA_POISSON):
         padded.fill_(-7)
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
-                 status, sampler, None, scratch, words, nat.stream_ptr(dev))
+                 status, sampler, scratch, words, nat.stream_ptr(dev))
         assert torch.all(padded[:, G:] == -7)
         if sampler == nat.SAMPLER_HYBRID:
             assert torch.equal(padded[:, :G], dense)
@@ -714,13 +716,13 @@ def test_padded_row_stride_and_raw_abi_call():
     # invalid arguments are reported through the status code / pst_last_error, not a crash
     with pytest.raises(ValueError):
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, G - 1,
-                 status, nat.SAMPLER_HYBRID, None, scratch, words, nat.stream_ptr(dev))
+                 status, nat.SAMPLER_HYBRID, scratch, words, nat.stream_ptr(dev))
     with pytest.raises(ValueError):
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
-                 status, 7, None, scratch, words, nat.stream_ptr(dev))
-    with pytest.raises(ValueError):                        # the hybrid sampler insists on its scratch list
+                 status, 7, scratch, words, nat.stream_ptr(dev))
+    with pytest.raises(ValueError):                        # the scratch must have the advertised size
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
-                 status, nat.SAMPLER_HYBRID, None, scratch, words - 1, nat.stream_ptr(dev))
+                 status, nat.SAMPLER_HYBRID, scratch, words - 1, nat.stream_ptr(dev))
 
 
 def test_api_variants_from_the_notebooks():
@@ -821,13 +823,26 @@ def test_density_index_matches_numpy_searchsorted_at_scale():
              nat.stream_ptr(dev))
     want = np.searchsorted(cdf, u, side="right")
     assert np.array_equal(rows.cpu().numpy(), np.minimum(want, P - 1))
-    # cells grouped by row: a permutation, non-decreasing in row
-    order = torch.empty(n, dtype=torch.int32, device=dev)
-    bins = torch.empty(P, dtype=torch.int32, device=dev)
-    nat.call("pst_group_cells_by_row", rows, n, P, bins, order, nat.stream_ptr(dev))
-    o = order.cpu().numpy()
+    # the visiting order pst_draw_counts builds from these rows: a permutation of the cells, non-decreasing
+    # in row, cut into groups of at most 64 cells of ONE row that tile [0, n)
+    G = 8
+    t = _flat_tree(np.ones(G), reps=P)
+    eng = CountEngine(t, TreeTables(t, dev), np.full(G, 0.2), np.full(G, 2.0), dev, sampler="hybrid")
+    eng.draw(rows, torch.ones(n, dtype=torch.float32, device=dev), 1, 0)
+    eng.check()
+    lay = (ctypes.c_int64 * 6)()
+    assert nat.load().pst_draw_scratch_layout(n, G, P, lay) == 0
+    sc = eng._scratch.cpu().numpy().view(np.uint32)
+    o = sc[lay[1]:lay[1] + n].astype(np.int64)
+    rr = rows.cpu().numpy()
     assert np.array_equal(np.sort(o), np.arange(n))
-    assert np.all(np.diff(rows.cpu().numpy()[o]) >= 0)
+    assert np.all(np.diff(rr[o]) >= 0)
+    ng = int(sc[1])
+    grp = sc[lay[4]:lay[4] + 4 * ng].reshape(ng, 4).astype(np.int64)
+    assert ng <= lay[5] and grp[0, 0] == 0 and np.all(grp[:, 1] >= 1) and np.all(grp[:, 1] <= 64)
+    assert np.array_equal(grp[1:, 0], (grp[:, 0] + grp[:, 1])[:-1]) and grp[-1, 0] + grp[-1, 1] == n
+    for pos0, cells, row, _ in grp[:: max(1, ng // 500)]:
+        assert np.all(rr[o[pos0:pos0 + cells]] == row)
 
 
 def test_count_stats_kernel_matches_numpy():
@@ -1206,23 +1221,28 @@ def test_inversion_far_tail_mass_is_pinned_from_both_sides():
 
 def test_sampler_parameterisation_f32_matches_get_pr_umi():
     """The arithmetic the sampler REALLY runs (fp32, MUFU rcp/lg2, small-theta series), exported through
-    pst_nb_params_f32 which calls the same __device__ functions as the draw kernel, against the
-    reference's get_pr_umi (count_model.py:156-161) in fp64: rel 1e-5 (north-star bar for fp32)."""
+    pst_nb_params_f32 which calls the same __device__ functions as the draw kernel in the same order
+    (mu = M s, theta = (alpha M) s + beta - 1), against the reference's get_pr_umi
+    (count_model.py:156-161) in fp64: rel 1e-5 (north-star bar for fp32)."""
     rng = np.random.RandomState(77)
     n = 200_000
-    m = np.exp(rng.uniform(np.log(1e-6), np.log(1e4), size=n))
+    M = np.exp(rng.uniform(np.log(1e-6), np.log(1e4), size=n))
+    sc = np.exp(rng.normal(0.0, 0.7, size=n))
     a = np.exp(rng.normal(np.log(0.2), 1.0, size=n))
     b = 1 + np.exp(rng.normal(0.0, 1.5, size=n))
-    # corners: Poisson limit, series range theta < 0.1, tiny means, the route thresholds, large shapes
-    m = np.concatenate([m, [1e-30, 3.0, 50.0, 31.999, 32.001, 20.0, 10.0, 30.0, 30.0, 5.0]])
-    a = np.concatenate([a, [0.2, 0.0, 0.0, 0.05, 0.05, 0.9, 3.0, 0.001, 0.02, 0.001]])
-    b = np.concatenate([b, [2.0, 1 + 1e-8, 1 + 1e-8, 1.5, 1.5, 2.0, 2.0, 1.3, 1.2, 1.05]])
-    got = cm.sampler_params_f32(a, b, m, device=DEV)
-    # reference in fp64 from the fp32-rounded inputs the kernel sees (alpha, beta-1, mu are fp32 tables)
-    m32, a32 = m.astype(np.float32).astype(np.float64), a.astype(np.float32).astype(np.float64)
-    bm32 = (b - 1.0).astype(np.float32).astype(np.float64)
+    # corners: Poisson limit, series range theta < 0.1, tiny means, the route thresholds, large shapes, theta > 32
+    M = np.concatenate([M, [1e-30, 3.0, 50.0, 31.99, 32.01, 19.9, 10.0, 30.0, 30.0, 5.0, 1.0]])
+    sc = np.concatenate([sc, np.ones(11)])
+    a = np.concatenate([a, [0.2, 0.0, 0.0, 0.05, 0.05, 0.9, 3.0, 0.001, 0.02, 0.001, 100.0]])
+    b = np.concatenate([b, [2.0, 1 + 1e-8, 1 + 1e-8, 1.5, 1.5, 2.0, 2.0, 1.3, 1.2, 1.05, 2.0]])
+    got = cm.sampler_params_f32(a, b, M, sc, device=DEV)
+    # reference in fp64 from the fp32-rounded inputs the kernel sees (alpha, beta-1, M, s are fp32)
+    f32 = lambda x: np.asarray(x).astype(np.float32).astype(np.float64)      # noqa: E731
+    m32 = f32(M) * f32(sc)
+    a32, bm32 = f32(a), f32(b - 1.0)
     p_ref, r_ref = orc.get_pr_umi(a32, bm32 + 1.0, m32)           # p = (s2-m)/s2 = q ; r = m^2/(s2-m)
     theta = a32 * m32 + bm32
+    assert np.allclose(got["mu"], m32, rtol=1e-6, atol=0)
     assert np.allclose(got["theta"], theta, rtol=2e-6, atol=0)
     assert np.allclose(got["q"], p_ref, rtol=1e-5, atol=0)
     # r = m/theta; get_pr_umi forms m^2/(s2-m) = m^2/(theta m) in fp64: identical up to fp64 cancellation
@@ -1236,15 +1256,17 @@ def test_sampler_parameterisation_f32_matches_get_pr_umi():
     # absolute bar on the exponent: the pmf's common factor 2^err must stay within the 2^-15 stretch
     assert np.max(np.abs(got["log2p0"][inv] - l2[inv])) < 2e-5, np.max(np.abs(got["log2p0"][inv] - l2[inv]))
     assert np.allclose(got["log2p0"], l2, rtol=1e-5, atol=2e-5)
-    # routes: inversion iff mean <= 32, variance <= 400, and (shape <= 48 or theta < 0.1)
+    # routes: inversion iff mean <= 32, variance <= 400, theta <= 32 and (shape <= 48 or theta < 0.1)
     var = m32 * (1 + theta)
-    want = (m32 <= 32) & (var <= 400) & ((m32 / theta <= 48) | (theta < 0.1))
-    edge = (np.abs(m32 - 32) < 1e-3) | (np.abs(var - 400) < 0.05) | (np.abs(m32 / theta - 48) < 0.01) | \
-        (np.abs(theta - 0.1) < 1e-5)
-    assert np.array_equal(inv[~edge], want[~edge])
-    assert got["route"][-10:].tolist() == [1, 1, 0, 1, 0, 1, 1, 0, 1, 1], got["route"][-10:].tolist()
-    bad = cm.sampler_params_f32([0.2, 0.2, -1.0], [2.0, 0.5, 2.0], [0.0, 1.0, 1.0], device=DEV)
-    assert bad["route"].tolist() == [2, 2, 2]
+    shape = m32 / theta
+    want = (m32 <= 32) & (var <= 400) & ((shape <= 48) | (theta < 0.1)) & (theta <= 32)
+    edge = (np.abs(m32 / 32 - 1) < 1e-4) | (np.abs(var / 400 - 1) < 1e-4) | (np.abs(shape / 48 - 1) < 1e-3) | \
+        (np.abs(theta / 0.1 - 1) < 1e-4) | (np.abs(theta / 32 - 1) < 1e-4)
+    assert edge.mean() < 0.01 and np.array_equal(inv[~edge], want[~edge])
+    assert got["route"][-11:].tolist() == [1, 1, 0, 1, 0, 1, 1, 0, 1, 1, 0], got["route"][-11:].tolist()
+    bad = cm.sampler_params_f32([0.2, 0.2, -1.0, 0.2], [2.0, 0.5, 2.0, 2.0], [0.0, 1.0, 1.0, 1.0], [1.0, 1.0, 1.0, -1.0],
+                                device=DEV)
+    assert bad["route"].tolist() == [2, 2, 2, 2]
 
 
 def test_empty_and_ragged_partitions():

@@ -185,6 +185,23 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("no oracle", ""), f
 
 
+def test_text_writers_match_files_written_by_the_reference(tmp_path):
+    """Byte-for-byte: tests/golden/written_files.json holds what the reference's own writers
+    (tree_utils.py:59-173) produce for conftest.writer_inputs()."""
+    import json
+    from conftest import writer_inputs
+    X, uMs, H, labs, brns, scal, gscale, alpha, beta = writer_inputs()
+    t = ptree.Tree(topology=[["A", "B"]], time={"A": 3, "B": 2}, num_branches=2, branch_points=0, modules=2, G=5)
+    tu.save_matrices("job", str(tmp_path), X, uMs, H)
+    tu.save_cell_params("job", str(tmp_path), labs, brns, scal)
+    tu.save_gene_params("job", str(tmp_path), gscale, alpha, beta)
+    tu.save_params("job", str(tmp_path), t, 7)
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "written_files.json")))
+    assert sorted(os.listdir(tmp_path)) == sorted(want)
+    for name, text in want.items():
+        assert open(tmp_path / name).read() == text, name
+
+
 def test_text_writers_round_trip(tmp_path):
     """tree_utils.save_* write the reference's file set (tree_utils.py:59-173)."""
     import pandas as pd
