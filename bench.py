@@ -543,27 +543,50 @@ def run_e2e(a, tree, alpha, beta, sampler, dev, rank, world, barrier, max_over_r
     hco = torch.empty(ecells, dtype=torch.int32).pin_memory()
     hsc = torch.empty(ecells, dtype=torch.float64).pin_memory()
 
-    def run_pinned(x_dtype):
+    def run_pinned(x_dtype, transport=None):
         hX = torch.empty((ecells, G), dtype=x_dtype).pin_memory()
         overflow = {}
 
         def api_call(seed_):
             return sim.sample_density(tree, ecells * world, seed=seed_, dtype=np.int32,
-                                      host_out=(hX, hpt, hco, hsc, overflow), **api_kwargs())
+                                      host_out=(hX, hpt, hco, hsc, overflow), host_transport=transport, **api_kwargs())
         dt = clock(api_call, steps)
         listed = len(overflow.get("index", ()))
-        d2h = hX.numel() * hX.element_size() + ecells * (8 + 4 + 8) + listed * 12
+        from prosstt_b200.device import _shared_host_transport
+        eff = transport or _shared_host_transport()
+        width = {"u8": 1, "u16": 2}.get(eff, 4) if x_dtype == torch.int32 else hX.element_size()
+        d2h = hX.numel() * width + ecells * (8 + 4 + 8) + listed * 12
         return float(ecells) * G * world * steps / dt, d2h, listed
 
-    v32, d2h, _ = run_pinned(torch.int32)
+    v32, d2h, _ = run_pinned(torch.int32)                       # transport: library default for this host
+    v32d, _, _ = run_pinned(torch.int32, "direct") if world >= 4 else (v32, 0, 0)
     v16, d2h16, listed = run_pinned(torch.uint16)
     v8, d2h8, listed8 = run_pinned(torch.uint8)
+    # int32 host matrix, but the counts cross PCIe as uint8 + overflow list and host threads widen them
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, cores // max(1, world))
+    hX32 = torch.empty((ecells, G), dtype=torch.int32).pin_memory()
+
+    def via_u8(seed_):
+        return sim.sample_density(tree, ecells * world, seed=seed_, dtype=np.int32, host_out=(hX32, hpt, hco, hsc),
+                                  host_transport="u8", host_threads=threads, **api_kwargs())
+    dt = clock(via_u8, steps)
+    v32u8 = float(ecells) * G * world * steps / dt
     return {"value": v32, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "cells_per_step_per_gpu": ecells, "steps": steps,
             "note": "simulation.sample_density(tree, N, alpha, beta, host_out=pinned buffers): tree tables, "
                     "cdf and gene parameters uploaded per call; int32 counts + pseudotime + branch + "
                     "scalings land in host memory (chunked, copy overlapped with sampling)",
+            "int32_direct": {"value": v32d, "unit": UNIT,
+                             "note": "`value` with host_transport='direct' (int32 over PCIe, written by the copy engine); "
+                                     "the library default is 'direct' for up to 3 ranks per host and 'u8' above"},
             "default_api": default_api,
+            "int32_via_u8": {"value": v32u8, "unit": UNIT, "host_threads_per_rank": threads, "host_cores": cores,
+                             "d2h_bytes_per_step": int(d2h8),
+                             "note": "same int32 pinned host matrix as `value`, but the counts cross PCIe as uint8 + "
+                                     "exact overflow list into pinned staging and host threads (pst_host_widen, "
+                                     "pst_host_apply_overflow) expand them: a quarter of the PCIe bytes, 4 B/count of "
+                                     "host-memory writes by the CPU instead of by DMA"},
             "narrow_u16": {"value": v16, "unit": UNIT, "d2h_bytes_per_step": int(d2h16),
                            "overflow_entries_last_step": int(listed),
                            "note": "same call with a uint16 host matrix: min(count, 65535) plus an exact "

@@ -207,7 +207,11 @@ int pst_nb_params_f32(const float *M, const float *scaling, const float *alpha, 
  * warps share means rows; built by four small kernels in front of the draw, it never changes the
  * counts - and (b) the list of the counts whose uniform lies in the top 2^-14 (about 6e-5 n G
  * entries of 16 bytes), which a last small kernel inverts with a 64-bit uniform against a cdf
- * accumulated in fp64: that is what resolves the upper tail beyond the 1 - 1e-7 quantile. */
+ * accumulated in fp64: that is what resolves the upper tail beyond the 1 - 1e-7 quantile.
+ * gene_sum / gene_sumsq / gene_zeros (all three or all NULL; G entries each, ADDED to: the caller
+ * zeroes them): per-gene sum, sum of squares and number of zeros of this call's counts, fused into
+ * the draw (each warp sums its tile of X from L2 right after writing it) - the per-gene half of
+ * pst_count_stats without the second pass over the matrix, bit-identical to it. */
 int64_t pst_draw_scratch_words(int64_t n, int64_t G, int64_t P);
 /* Word offsets inside that scratch (debugging / tests): h_out[0] = capacity of the tail list (entries
  * of 4 words from word 4; word 0 counts them), [1] = order[n] (cells in visiting order), [2] =
@@ -219,7 +223,8 @@ int pst_draw_counts(const float *means, int64_t P, int64_t G,
                     const float *alpha, const float *beta_m1,
                     uint64_t seed, int64_t cell0, int64_t n,
                     int32_t *X, int64_t ldx, uint32_t *flags, int32_t sampler,
-                    uint32_t *scratch, int64_t scratch_words, void *stream);
+                    uint32_t *scratch, int64_t scratch_words,
+                    uint64_t *gene_sum, uint64_t *gene_sumsq, uint64_t *gene_zeros, void *stream);
 
 /* One streaming pass over a count matrix X[n][ldx] (first G columns): per-cell total counts and
  * zero counts, per-gene sum, sum of squares and zero counts.  These are the summaries the

@@ -47,7 +47,8 @@ _SIGNATURES = {
     "pst_nb_params_f32": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pst_draw_scratch_words": (_i64, [_i64, _i64, _i64]),
     "pst_draw_scratch_layout": (C.c_int, [_i64, _i64, _i64, _p]),
-    "pst_draw_counts": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _u64, _i64, _i64, _p, _i64, _p, _i32, _p, _i64, _p]),
+    "pst_draw_counts": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _u64, _i64, _i64, _p, _i64, _p, _i32, _p, _i64,
+                                  _p, _p, _p, _p]),
     "pst_count_stats": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "pst_transform_counts": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _p, _i64, _p]),
     "pst_csr_fill": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),

@@ -271,7 +271,7 @@ struct HyWarpQueues {
   int2 lw[HY_LCAP];         //                 where the count goes
   float4 ge[HY_MCAP];       // mixture: mu (or lambda once the gamma is accepted), theta, cell, gene
   int ga[HY_MCAP];          //          attempt counter of the current stage | stage << 16
-  int fill[4];              // [0] search entries (appended with shared-memory atomics), [1] long searches
+  int fill[4];              // [0] search entries (appended with shared-memory atomics), [1] long searches, [2] mixture entries
 };
 
 #ifndef HY_MIN_CTAS
@@ -279,6 +279,13 @@ struct HyWarpQueues {
 #endif
 #ifndef HY_ENQ_ATOMIC
 #define HY_ENQ_ATOMIC 1   // search-queue slots from a shared-memory counter (1) or from ballots (0)
+#endif
+#ifndef HY_MIX_ATOMIC
+#define HY_MIX_ATOMIC 0   // mixture-queue slots: one atomic per lane (1) or ballots (0); measured equal at the bench
+                          // depth, ballots better when every count takes the mixture (gamma_poisson sampler)
+#endif
+#ifndef HY_STAT_ROWS
+#define HY_STAT_ROWS 4    // rows of the chunk's tile in flight while the fused per-gene summaries are formed
 #endif
 #ifndef HY_CHUNK_CELLS
 #define HY_CHUNK_CELLS 64                    // most cells per chunk (x 32 quads = 8192 counts); all of one tree row
@@ -295,14 +302,15 @@ struct HyWarpQueues {
 // atomic counter, so warps whose queues drain more often simply take fewer of them; consecutive
 // chunk ids are adjacent strips of the same cells (neighbouring warps complete the same X rows
 // together), and concurrently running warps share means rows in L2.
-template <int KFIX, bool VEC, bool ALL_MIX>
+template <int KFIX, bool VEC, bool ALL_MIX, bool STATS>
 __global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
 draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, uint32_t G, uint32_t Q,
                    const float *__restrict__ scaling, const float *__restrict__ alpha,
                    const float *__restrict__ beta_m1, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx,
                    uint32_t *__restrict__ flags, const uint32_t *__restrict__ hdr,
                    const int32_t *__restrict__ order, const uint4 *__restrict__ groups, int sched,
-                   uint32_t *__restrict__ tail, uint32_t tail_cap) {
+                   uint32_t *__restrict__ tail, uint32_t tail_cap, unsigned long long *__restrict__ gene_sum,
+                   unsigned long long *__restrict__ gene_sumsq, unsigned long long *__restrict__ gene_zeros) {
   __shared__ HyWarpQueues queues[HY_WARPS];
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -320,6 +328,18 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
   __syncwarp();
 
 
+  // Write a finished search.  With fused summaries (STATS) an entry whose chunk has already been summed
+  // carries bit 31 in its gene word: the sum saw the partial count KFIX there, the difference is added now.
+  auto finish_search = [&](int2 w, int cn) {
+    const uint32_t gene = (uint32_t)w.y & 0x7fffffffu;
+    X[(uint64_t)(uint32_t)w.x * ldx + gene] = cn;
+    if constexpr (STATS) {
+      if (w.y < 0) {
+        atomicAdd(gene_sum + gene, (unsigned long long)(cn - KFIX));
+        atomicAdd(gene_sumsq + gene, (unsigned long long)cn * (unsigned long long)cn - (unsigned long long)(KFIX * KFIX));
+      }
+    }
+  };
   // the open-ended part of a search, 32 long searches at a time: P(k) form from k = HY_TAIL0, a + q k
   // advanced by one FADD per term, 1/(k+1) from the constant bank, a vote every 4 terms
   auto drain_long = [&](int first, int cnt) {
@@ -349,7 +369,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
     }
     // every u handled here lies below 1 - 2^-15 < T, the top of the computed cdf, and cdf - u is
     // accumulated (exact near the crossing), so each search ends; HY_KMAX only bounds the loop
-    if (act) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
+    if (act) finish_search(w, cn);
   };
   // finish up to 32 queued inversions at full warp width; k is warp-uniform
   auto drain_search = [&](int first, int cnt) {
@@ -374,7 +394,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
     // width instead of once per batch for one or two lanes.
     const bool open = act && (dd < 0.f);
     const unsigned mo = __ballot_sync(0xffffffffu, open);
-    if (act && !open) X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
+    if (act && !open) finish_search(w, cn);
     if (mo) {
       int nl = *(volatile int *)&wq.fill[1];
       if (nl + __popc(mo) > HY_LCAP) { drain_long(0, nl); nl = 0; __syncwarp(); }   // rare: make room
@@ -399,7 +419,8 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
     int ga = 0;                                     // attempt | stage << 16 (stage 1: x holds lambda)
     if (act) { g = wq.ge[first + lane]; ga = wq.ga[first + lane]; }
     __syncwarp();                                   // every entry is read before slots are reused
-    const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w);
+    const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w) & 0x7fffffff;
+    const bool summed = __float_as_int(g.w) < 0;    // STATS: the chunk was summed with 0 in this element
     const bool have_lambda = (ga >> 16) != 0;
     const int att = ga & 0xffff;
     int status = MIX_DONE;
@@ -416,6 +437,13 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         int val = (int)value;
         if (value > 2147483520.f) { val = 2147483647; flag |= PST_FLAG_CLAMPED; }
         X[(uint64_t)(uint32_t)ccell * ldx + (uint32_t)gene] = val;
+        if constexpr (STATS) {
+          if (summed && val > 0) {
+            atomicAdd(gene_sum + gene, (unsigned long long)val);
+            atomicAdd(gene_sumsq + gene, (unsigned long long)val * (unsigned long long)val);
+            atomicAdd(gene_zeros + gene, ~0ull);             // minus one
+          }
+        }
       }
     }
     const bool again = act && status != MIX_DONE;
@@ -553,9 +581,29 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       // large means: queue them for the mixture now, so mu/theta are dead during the head.  Many
       // (cell, strip) pairs have none: one vote skips the block
       if (ALL_MIX || __any_sync(0xffffffffu, !(small[0] && small[1] && small[2] && small[3]))) {
+#if HY_MIX_ATOMIC
+        // a lane reserves the slots of its (up to four) entries with one shared-memory atomic
+        bool tm[4];
+        int nm = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tm[j] = !small[j] && (VEC || g0 + j < G) && (!STATS || lane_first); nm += tm[j] ? 1 : 0; }
+        if (nm) {
+          int e = atomicAdd(&wq.fill[2], nm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (tm[j]) {
+              wq.ge[e] = make_float4(mu[j], th[j], __int_as_float((int)cell), __int_as_float((int)(g0 + j)));
+              wq.ga[e] = 0;
+              ++e;
+            }
+          }
+        }
+        __syncwarp();
+        ng = *(volatile int *)&wq.fill[2];
+#else
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool to_mix = !small[j] && (VEC || g0 + j < G);
+          const bool to_mix = !small[j] && (VEC || g0 + j < G) && (!STATS || lane_first);
           const unsigned mg = __ballot_sync(0xffffffffu, to_mix);
           if (to_mix) {
             const int e = ng + __popc(mg & lt_mask);
@@ -564,6 +612,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
           }
           ng += __popc(mg);
         }
+#endif
       }
       // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
       if constexpr (!ALL_MIX) {
@@ -581,6 +630,10 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       // drained, which always writes them (the __syncwarp below orders this store before the drain's)
       {
         int32_t *dst = X + ((uint64_t)(uint32_t)cell * ldx + g0);
+        if constexpr (STATS) {                      // the summation reads mixture slots before their drain: 0 there
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cnt[j] = small[j] ? cnt[j] : 0;
+        }
         if (VEC) {
           *reinterpret_cast<int4 *>(dst) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
         } else {
@@ -595,7 +648,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         // slots come from a shared-memory counter
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if ((VEC || g0 + j < G) && small[j] && (d[j] < 0.f)) {
+          if ((VEC || g0 + j < G) && small[j] && (d[j] < 0.f) && (!STATS || lane_first)) {
             const int e = atomicAdd(&wq.fill[0], 1);
             wq.se[e] = make_float4(t[j], d[j], a[j], q[j]);     // t = P(KFIX-1) (KFIX-1)!, rescaled in the drain
             wq.sw[e] = make_int2((int)cell, (int)(g0 + j));
@@ -607,7 +660,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         // slots from ballots (all lanes take part)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool push = (VEC || g0 + j < G) && small[j] && (d[j] < 0.f);
+          const bool push = (VEC || g0 + j < G) && small[j] && (d[j] < 0.f) && (!STATS || lane_first);
           const unsigned ms = __ballot_sync(0xffffffffu, push);
           if (push) {
             const int e = ns + __popc(ms & lt_mask);
@@ -627,7 +680,65 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
 #if HY_ENQ_ATOMIC
         if (lane == 0) wq.fill[0] = ns;
 #endif
+#if HY_MIX_ATOMIC
+        if (lane == 0) wq.fill[2] = ng;
+#endif
         __syncwarp();
+      }
+    }
+    if constexpr (STATS) {
+      // Per-gene summaries fused into the draw (the notebooks' X.sum(axis=0), per-gene variance and zero
+      // fraction; pst_count_stats as a second pass costs a quarter of the draw).  The lane adds up its four
+      // genes over the chunk's tile of X (64 cells x 512 bytes, written by this warp and still in L2): one
+      // atomic per gene and chunk.  The few elements that are not final yet are corrected when they are:
+      // counts on the tail list by tail_fix_kernel, queued entries by their drain.
+      // (entries still queued are summed with their partial value - KFIX for a search, 0 for the mixture -
+      // and marked: their drain adds the difference, see finish_search / drain_mixture)
+      __syncwarp();
+      {
+        const int nl = *(volatile int *)&wq.fill[1];
+        for (int i = lane; i < ns; i += 32) wq.sw[i].y |= (int)0x80000000;
+        for (int i = lane; i < nl; i += 32) wq.lw[i].y |= (int)0x80000000;
+        for (int i = lane; i < ng; i += 32) wq.ge[i].w = __int_as_float(__float_as_int(wq.ge[i].w) | (int)0x80000000);
+      }
+      __syncwarp();
+      unsigned long long sq[4] = {0, 0, 0, 0}, sm[4] = {0, 0, 0, 0};
+      unsigned int nz[4] = {0, 0, 0, 0};                   // nonzero counts; zeros = cells - nz
+      for (int c0 = 0; c0 < n_cells; c0 += HY_STAT_ROWS) {
+        if ((c0 & 31) == 0) meta_cell = order[pos0 + (uint32_t)min(c0 + lane, n_cells - 1)];
+        unsigned int v[HY_STAT_ROWS][4];
+#pragma unroll
+        for (int i = 0; i < HY_STAT_ROWS; ++i) {            // row loads in flight
+          const int32_t cell = __shfl_sync(0xffffffffu, meta_cell, (c0 + i) & 31);
+          const int32_t *row = X + ((uint64_t)(uint32_t)cell * ldx + g0);
+          const bool in = c0 + i < n_cells;
+          if (VEC) {
+            const int4 x = in ? __ldcg(reinterpret_cast<const int4 *>(row)) : make_int4(0, 0, 0, 0);
+            v[i][0] = (unsigned)x.x; v[i][1] = (unsigned)x.y; v[i][2] = (unsigned)x.z; v[i][3] = (unsigned)x.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[i][j] = (in && g0 + j < G) ? (unsigned)__ldcg(row + j) : 0u;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < HY_STAT_ROWS; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                     // rows past the group read as 0: nothing added
+            sm[j] += v[i][j];                                // one IMAD.WIDE each (64-bit accumulate)
+            sq[j] += (unsigned long long)v[i][j] * v[i][j];
+            nz[j] += min(v[i][j], 1u);
+          }
+        }
+      }
+      if (lane_first) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (VEC || g0 + j < G) {
+            atomicAdd(gene_sum + g0 + j, sm[j]);
+            atomicAdd(gene_sumsq + g0 + j, sq[j]);
+            atomicAdd(gene_zeros + g0 + j, (unsigned long long)((unsigned)n_cells - nz[j]));
+          }
+        }
       }
     }
   }
@@ -673,13 +784,21 @@ __global__ void nb_params_f32_kernel(const float *__restrict__ M, const float *_
 
 // The counts the draw kernel listed for the fp64 tail path, one thread each.  tail[0] = number of
 // entries, entries (cell, gene, mu, theta) from word 4 on.
+// With fused per-gene summaries the draw kernel has counted these elements as zeros: corrected here.
 __global__ void tail_fix_kernel(const __grid_constant__ PhiloxKey key, const uint32_t *__restrict__ tail,
-                                uint32_t tail_cap, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx) {
+                                uint32_t tail_cap, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx,
+                                unsigned long long *__restrict__ gene_sum, unsigned long long *__restrict__ gene_sumsq,
+                                unsigned long long *__restrict__ gene_zeros) {
   const uint32_t n = min(tail[0], tail_cap);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint4 e = reinterpret_cast<const uint4 *>(tail + 4)[i];
-    X[(uint64_t)e.x * ldx + e.y] =
-        invert_tail(__uint_as_float(e.z), __uint_as_float(e.w), key.k0[0], key.k1[0], e.y, cell0 + (int64_t)e.x);
+    const int k = invert_tail(__uint_as_float(e.z), __uint_as_float(e.w), key.k0[0], key.k1[0], e.y, cell0 + (int64_t)e.x);
+    X[(uint64_t)e.x * ldx + e.y] = k;
+    if (gene_sum != nullptr && k > 0) {
+      atomicAdd(gene_sum + e.y, (unsigned long long)k);
+      atomicAdd(gene_sumsq + e.y, (unsigned long long)k * (unsigned long long)k);
+      atomicAdd(gene_zeros + e.y, ~0ull);                   // minus one
+    }
   }
 }
 
@@ -942,8 +1061,11 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
                                const float *scaling, const float *alpha, const float *beta_m1,
                                uint64_t seed, int64_t cell0, int64_t n, int32_t *X, int64_t ldx,
                                uint32_t *flags, int32_t sampler, uint32_t *scratch, int64_t scratch_words,
-                               void *stream) {
+                               uint64_t *gene_sum, uint64_t *gene_sumsq, uint64_t *gene_zeros, void *stream) {
   const char *fn = "pst_draw_counts";
+  const bool stats = gene_sum || gene_sumsq || gene_zeros;
+  PST_REQUIRE(!stats || (gene_sum && gene_sumsq && gene_zeros), fn,
+              "the fused per-gene summaries come as a set: pass all three arrays or none");
   PST_REQUIRE(P >= 0 && G >= 0 && n >= 0 && cell0 >= 0, fn, "negative size");
   PST_REQUIRE(ldx >= G, fn, "ldx < G");
   PST_REQUIRE(G < (int64_t)1 << 31 && P < (int64_t)1 << 31 && ldx < (int64_t)1 << 32, fn,
@@ -994,14 +1116,17 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const int64_t cap = (int64_t)num_sm() * HY_MIN_CTAS;
   const unsigned hb = (unsigned)(need < cap ? need : cap);
   const uint32_t tail_cap = (uint32_t)L.tail_cap;
+  typedef unsigned long long ull;
+#define PST_LAUNCH_DRAW2(V, MIX, ST)                                                                                \
+    draw_counts_kernel<HY_KFIX, V, MIX, ST><<<hb, HY_THREADS, 0, st>>>(                                             \
+        PhiloxKey(seed), means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags,  \
+        scratch, order, groups, slot, scratch, tail_cap, (ull *)gene_sum, (ull *)gene_sumsq, (ull *)gene_zeros)
 #define PST_LAUNCH_DRAW(MIX)                                                                                        \
   do {                                                                                                              \
-    if (vec) draw_counts_kernel<HY_KFIX, true, MIX><<<hb, HY_THREADS, 0, st>>>(                                     \
-        PhiloxKey(seed), means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags,  \
-        scratch, order, groups, slot, scratch, tail_cap);                                                           \
-    else draw_counts_kernel<HY_KFIX, false, MIX><<<hb, HY_THREADS, 0, st>>>(                                        \
-        PhiloxKey(seed), means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags,  \
-        scratch, order, groups, slot, scratch, tail_cap);                                                           \
+    if (vec && stats) PST_LAUNCH_DRAW2(true, MIX, true);                                                            \
+    else if (vec) PST_LAUNCH_DRAW2(true, MIX, false);                                                               \
+    else if (stats) PST_LAUNCH_DRAW2(false, MIX, true);                                                             \
+    else PST_LAUNCH_DRAW2(false, MIX, false);                                                                       \
   } while (0)
   if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
     PST_LAUNCH_DRAW(true);
@@ -1009,11 +1134,13 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   }
   PST_LAUNCH_DRAW(false);
 #undef PST_LAUNCH_DRAW
+#undef PST_LAUNCH_DRAW2
   rc = check_launch(fn);
   if (rc) return rc;
   // the listed counts (2^-14 of the inverted ones): one thread each, grid-stride beyond the expectation
   const int64_t expect = (int64_t)((double)n * (double)G / 16384.0) + 256;
   const unsigned tb = (unsigned)std::min<int64_t>((expect + 127) / 128, (int64_t)num_sm() * 16);
-  tail_fix_kernel<<<tb, 128, 0, st>>>(PhiloxKey(seed), scratch, tail_cap, cell0, X, (uint32_t)ldx);
+  tail_fix_kernel<<<tb, 128, 0, st>>>(PhiloxKey(seed), scratch, tail_cap, cell0, X, (uint32_t)ldx, (ull *)gene_sum,
+                                      (ull *)gene_sumsq, (ull *)gene_zeros);
   return check_launch(fn);
 }

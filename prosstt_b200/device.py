@@ -199,6 +199,23 @@ _STAGE_BYTES = 256 << 20                      # one pinned staging buffer (two p
 _STAGING = {}
 
 
+def _shared_host_transport():
+    """Transport of an int32 pinned host matrix when nothing was asked for.  One GPU per host: "direct"
+    (the copy engine writes the matrix, PCIe-bound at ~14e9 counts/s).  Several ranks on one host
+    (torchrun's LOCAL_WORLD_SIZE >= 4) share the host's PCIe root / memory system - 8 B200s of one box
+    reach 93 GB/s together, 2.3e10 counts/s as int32 - so the counts cross as uint8 + overflow list and
+    each rank's share of the host cores widens them (measured: profiles/r02_host_bw_8gpu.txt).
+    PST_HOST_TRANSPORT=direct|i32|u16|u8 overrides."""
+    forced = os.environ.get("PST_HOST_TRANSPORT")
+    if forced:
+        return forced
+    try:
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    except ValueError:
+        local_world = 1
+    return "u8" if local_world >= 4 else "direct"
+
+
 def _pinned_staging(dev, nbytes):
     """Two pinned host buffers of at least nbytes for the staged device->host path, allocated once per
     device and kept (page-locking costs ~0.2 s per GB)."""
@@ -227,9 +244,12 @@ class CountEngine(object):
         self._scratch = None
         self.overflow = None                                    # filled by draw_to_host (uint16 format)
 
-    def draw(self, rows, scaling32, seed, cell0, out=None):
+    def draw(self, rows, scaling32, seed, cell0, out=None, gene_stats=None):
         """Sample X for the cells described by rows/scaling32 (device tensors); global
-        index of the first cell is cell0.  Returns an (n, G) int32 device tensor."""
+        index of the first cell is cell0.  Returns an (n, G) int32 device tensor.
+        gene_stats: dict with int64 (G,) device tensors "gene_sum", "gene_sumsq", "gene_zeros"
+        (stats.new_gene_stats) that the draw adds this call's per-gene summaries to - fused into
+        the kernel, no second pass over the matrix; equals stats.count_stats(X) bit for bit."""
         n = int(rows.numel())
         if out is None:
             out = torch.empty((n, self.G), dtype=torch.int32, device=self.dev)
@@ -246,7 +266,9 @@ class CountEngine(object):
         nat.call("pst_draw_counts", nat.ptr(self.means), self.P, self.G, nat.ptr(rows),
                  nat.ptr(scaling32), nat.ptr(self.alpha), nat.ptr(self.beta_m1),
                  seed, int(cell0), n, out.data_ptr(), out.stride(0) if n else self.G,
-                 nat.ptr(self.flags), self.sampler, self._scratch, words, st)
+                 nat.ptr(self.flags), self.sampler, self._scratch, words,
+                 *((gene_stats["gene_sum"], gene_stats["gene_sumsq"], gene_stats["gene_zeros"])
+                   if gene_stats is not None else (None, None, None)), st)
         if timers is not None:
             t1 = torch.cuda.Event(enable_timing=True)
             t1.record(torch.cuda.current_stream(self.dev))
@@ -284,11 +306,21 @@ class CountEngine(object):
             raise ValueError("host_out must be an int32, int64, uint16 or uint8 CPU matrix of shape (%d, %d)"
                              % (n, self.G))
         narrow_dst = hdt in (torch.uint16, torch.uint8)
+        if transport is None and not is_np and hdt == torch.int32 and pinned:
+            transport = _shared_host_transport()
         if transport in (None, "direct") and not is_np and hdt != torch.int64 and \
                 (pinned or narrow_dst or transport == "direct"):
             return self._draw_to_host_direct(rows, scaling32, seed, cell0, host_out, chunk_cells, overflow_cap)
         if narrow_dst:
             raise ValueError("a uint16 / uint8 host matrix must be a CPU tensor and takes transport 'direct'")
+        if not threads:
+            # several ranks on one host: each takes its share of the cores
+            try:
+                local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            except ValueError:
+                local_world = 1
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            threads = max(1, cores // local_world)
         return self._draw_to_host_staged(rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
                                          transport or "i32", threads)
 

@@ -76,12 +76,14 @@ class DensitySession(object):
         else:
             nat.call("pst_scalings", None, n, nat.ptr(self.s64), nat.ptr(self.s32), st)
 
-    def step(self, seed):
-        """One sample_density pass into the resident slab.  Stream-ordered, no sync."""
+    def step(self, seed, gene_stats=None):
+        """One sample_density pass into the resident slab.  Stream-ordered, no sync.  gene_stats
+        (stats.new_gene_stats): per-gene sum / sum of squares / zeros accumulated inside the draw."""
         self.index_and_scalings(seed)
         n = self.n
         self.t_draw[0].record()
-        self.engine.draw(self.rows[:n], self.s32[:n], nat.derive_seed(seed, 2), self.first, out=self.X[:n])
+        self.engine.draw(self.rows[:n], self.s32[:n], nat.derive_seed(seed, 2), self.first, out=self.X[:n],
+                         gene_stats=gene_stats)
         self.t_draw[1].record()
         return self.X[:n]
 

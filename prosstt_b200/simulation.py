@@ -424,7 +424,7 @@ def _sample_counts(engine, rows, s32, seed, first, dtype, out):
 
 
 def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
-                    seed, first, dev, dtype, out, sampler, host_out=None):
+                    seed, first, dev, dtype, out, sampler, host_out=None, host_transport=None, host_threads=0):
     """Common tail of every sampler (simulation.py:590-599): scalings, then counts.
     host_out = (X, pseudotime, branch_codes, scalings) preallocated CPU tensors (int32 (n,G),
     int64, int32, float64; ideally pinned): the counts are streamed into them in cell chunks
@@ -446,7 +446,8 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
         hpt.copy_(pt, non_blocking=True)
         hcodes.copy_(codes, non_blocking=True)
         hs.copy_(s64, non_blocking=True)
-        engine.draw_to_host(rows, s32, nat.derive_seed(seed, 2), first, hX)
+        engine.draw_to_host(rows, s32, nat.derive_seed(seed, 2), first, hX, transport=host_transport,
+                            threads=host_threads)
         torch.cuda.current_stream(dev).synchronize()
         engine.check()
         if engine.overflow is not None:
@@ -465,10 +466,13 @@ def _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mea
 
 def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, scale_mean=0.,
                    seed=None, device=None, shard=None, dtype=np.int64, out="numpy",
-                   sampler=DEFAULT_SAMPLER, uniforms=None, host_out=None):
+                   sampler=DEFAULT_SAMPLER, uniforms=None, host_out=None, host_transport=None, host_threads=0):
     """Sample `no_cells` (pseudotime, branch) pairs according to tree.density and draw
     their counts (simulation.py:416-471).  Returns (X, pseudotime, branches, scalings).
-    `uniforms` (one per cell) replays externally supplied draws through the index map."""
+    `uniforms` (one per cell) replays externally supplied draws through the index map.
+    host_transport ("direct", "i32", "u16", "u8"; with host_out): the format in which the counts cross
+    PCIe; the narrow ones are expanded into the int32 / int64 host matrix by `host_threads` host threads
+    (0 = all) together with their exact overflow list - the caller receives the same counts either way."""
     dev = nat.device(device)
     seed = nat.split_seed(seed)
     tables = TreeTables(tree, dev)
@@ -487,7 +491,8 @@ def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, s
     nat.call("pst_density_index", nat.ptr(cdf), tables.P, nat.ptr(u), n, nat.ptr(tables.d("pos_pt")),
              nat.ptr(tables.d("pos_branch")), nat.ptr(rows), nat.ptr(pt), nat.ptr(codes), st)
     return _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
-                           seed, lo, dev, dtype, out, sampler, host_out=host_out)
+                           seed, lo, dev, dtype, out, sampler, host_out=host_out, host_transport=host_transport,
+                           host_threads=host_threads)
 
 
 def cover_whole_tree(tree):
@@ -640,25 +645,19 @@ def draw_counts(tree, pseudotime, branches, scalings, alpha, beta, seed=None, de
 def add_non_diff_genes(inform_expr_matrix, genes, gene_params, cell_scalings, seed=None,
                        device=None, sampler=DEFAULT_SAMPLER):
     """Append `genes` constant-mean genes (mu = scaling * base_expr) to a count matrix
-    (simulation.py:654-675): the same NB kernel on a one-row means table."""
+    (simulation.py:654-675): the same NB kernel on a tree of one branch and one pseudotime step
+    whose means row is base_expr.  Returns a float64 (N, G + genes) array like the reference."""
+    from prosstt_b200.tree import Tree
     dev = nat.device(device)
     X0 = np.asarray(inform_expr_matrix)
     N, G = X0.shape
     base = np.asarray(gene_params["base_expr"], dtype=np.float64).reshape(1, genes)
-
-    class _Flat(object):
-        pass
-    flat = _Flat()
-    flat.G, flat.means, flat._device_cache = genes, {0: base}, {}
-    tables = _Flat()
-    tables.names, tables.P = [0], 1
-    tables.T, tables.row_base = np.array([1], np.int32), np.array([0], np.int32)
-    engine = CountEngine(flat, tables, gene_params["alpha"], gene_params["beta"], dev, sampler=sampler)
+    flat = Tree(topology=[], time={0: 1}, num_branches=1, branch_points=0, modules=1, G=genes)
+    flat.add_genes({0: base})
+    engine = CountEngine(flat, TreeTables(flat, dev), gene_params["alpha"], gene_params["beta"], dev, sampler=sampler)
     rows = torch.zeros(N, dtype=torch.int32, device=dev)
     s32 = nat.to_dev(cell_scalings, torch.float32, dev)
-    extra = engine.draw(rows, s32, nat.split_seed(seed), 0)
-    engine.check()
     fusion = np.zeros((N, G + genes))
     fusion[:, :G] = X0
-    fusion[:, G:] = extra.cpu().numpy()
+    fusion[:, G:] = _sample_counts(engine, rows, s32, nat.split_seed(seed), 0, np.int64, "numpy")
     return fusion

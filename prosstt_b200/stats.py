@@ -29,6 +29,12 @@ def count_stats(X):
     return out
 
 
+def new_gene_stats(G, device):
+    """Zeroed per-gene accumulators for the fused summaries of the draw (CountEngine.draw(gene_stats=...),
+    DensitySession.step(gene_stats=...)): they are added to, so one set can span many chunks or steps."""
+    return {k: torch.zeros(G, dtype=torch.int64, device=device) for k in ("gene_sum", "gene_sumsq", "gene_zeros")}
+
+
 def gene_mean_var(stats, n_cells):
     """Per-gene sample mean and (population) variance from count_stats output, as float64 tensors."""
     mean = stats["gene_sum"].double() / n_cells

@@ -551,6 +551,34 @@ def test_reference_script_flow_and_restricted_sampler():
     assert fused.shape == (80, 510) and np.array_equal(fused[:, :500], X)
 
 
+def test_add_non_diff_genes_distribution():
+    """The appended constant-mean genes (simulation.py:654-675): X[n, G+j] ~ NB(mean s_n base_j, variance
+    alpha_j mean^2 + beta_j mean).  Per-gene totals against the model (z-scores ~ N(0,1)), a two-sample KS
+    test per gene against numpy's legacy negative_binomial on the same (n, p) - what the reference's
+    nbinom.rvs() runs - and the informative block untouched."""
+    import scipy.stats
+    rng = np.random.RandomState(3)
+    N, G, extra = 20000, 7, 40
+    X0 = rng.poisson(2.0, size=(N, G))
+    sc = np.exp(rng.normal(0, 0.7, size=N))
+    gp = {"base_expr": np.exp(rng.normal(0.8, 1.0, size=extra)),
+          "alpha": np.exp(rng.normal(np.log(0.2), np.log(1.5), size=extra)),
+          "beta": np.exp(rng.normal(np.log(2.0), np.log(1.5), size=extra)) + 1}
+    F = sim.add_non_diff_genes(X0, extra, gp, sc, seed=5, device=DEV)
+    assert F.shape == (N, G + extra) and F.dtype == np.float64 and np.array_equal(F[:, :G], X0)
+    Y = F[:, G:]
+    assert np.array_equal(Y, np.round(Y)) and Y.min() >= 0
+    mu = sc[:, None] * gp["base_expr"][None, :]
+    var = gp["alpha"] * mu ** 2 + gp["beta"] * mu
+    z = (Y.sum(axis=0) - mu.sum(axis=0)) / np.sqrt(var.sum(axis=0))
+    assert abs(z.mean()) < 0.6 and 0.6 < z.std() < 1.4 and np.abs(z).max() < 4.5, (z.mean(), z.std())
+    p, r = orc.get_pr_umi(gp["alpha"], gp["beta"], mu)
+    ref = np.random.RandomState(99).negative_binomial(r, 1 - p)          # same (n, p) per cell and gene
+    ks = [scipy.stats.ks_2samp(Y[:, j], ref[:, j]).pvalue for j in range(extra)]
+    assert min(ks) > 1e-4 and np.median(ks) > 0.1, (min(ks), np.median(ks))
+    assert np.array_equal(F, sim.add_non_diff_genes(X0, extra, gp, sc, seed=5, device=DEV))   # reproducible
+
+
 # ------------------------------------------------------------------ sessions, named configs
 def test_density_session_equals_api_call():
     """The resident session (bench path) and simulation.sample_density give the same bits."""
@@ -706,7 +734,7 @@ def test_padded_row_stride_and_raw_abi_call():
     for sampler in (nat.SAMPLER_HYBRID, nat.SAMPLER_GAMMA_POISSON):
         padded.fill_(-7)
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
-                 status, sampler, scratch, words, nat.stream_ptr(dev))
+                 status, sampler, scratch, words, None, None, None, nat.stream_ptr(dev))
         assert torch.all(padded[:, G:] == -7)
         if sampler == nat.SAMPLER_HYBRID:
             assert torch.equal(padded[:, :G], dense)
@@ -716,13 +744,13 @@ def test_padded_row_stride_and_raw_abi_call():
     # invalid arguments are reported through the status code / pst_last_error, not a crash
     with pytest.raises(ValueError):
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, G - 1,
-                 status, nat.SAMPLER_HYBRID, scratch, words, nat.stream_ptr(dev))
+                 status, nat.SAMPLER_HYBRID, scratch, words, None, None, None, nat.stream_ptr(dev))
     with pytest.raises(ValueError):
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
-                 status, 7, scratch, words, nat.stream_ptr(dev))
+                 status, 7, scratch, words, None, None, None, nat.stream_ptr(dev))
     with pytest.raises(ValueError):                        # the scratch must have the advertised size
         nat.call("pst_draw_counts", eng.means, tb.P, G, rows, sc, eng.alpha, eng.beta_m1, 99, 5, n, padded, ldx,
-                 status, nat.SAMPLER_HYBRID, scratch, words - 1, nat.stream_ptr(dev))
+                 status, nat.SAMPLER_HYBRID, scratch, words - 1, None, None, None, nat.stream_ptr(dev))
 
 
 def test_api_variants_from_the_notebooks():
@@ -845,6 +873,37 @@ def test_density_index_matches_numpy_searchsorted_at_scale():
         assert np.all(rr[o[pos0:pos0 + cells]] == row)
 
 
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_fused_gene_stats_equal_the_second_pass(sampler):
+    """Per-gene sum, sum of squares and zero count accumulated inside pst_draw_counts (each warp sums its
+    tile of X right after writing it; the tail fix-up kernel corrects the few counts it rewrites) against
+    pst_count_stats on the finished matrix: bit for bit, incl. deep libraries (mixture-heavy), G not a
+    multiple of 4 or 128, ragged groups, and accumulation over several calls."""
+    from prosstt_b200.stats import count_stats, new_gene_stats
+    dev = torch.device(DEV)
+    rng = np.random.RandomState(12)
+    for G, n, depth in ((403, 3000, 0.0), (4096, 2500, 2.5), (8, 20000, 0.0), (1000, 700, 5.0)):
+        P = 37
+        t = ptree.Tree(topology=[], time={0: P}, num_branches=1, branch_points=0, modules=1, G=G)
+        t.add_genes({0: np.exp(rng.normal(0.5, 1.5, size=(P, G)))})
+        alpha = np.exp(rng.normal(np.log(0.2), 0.4, size=G))
+        beta = 1 + np.exp(rng.normal(0.0, 0.4, size=G))
+        eng = CountEngine(t, TreeTables(t, dev), alpha, beta, dev, sampler=sampler)
+        rows = _dev(rng.randint(0, P, size=n), torch.int32)
+        sc = _dev(np.exp(rng.normal(depth, 0.7, size=n)), torch.float32)
+        fused = new_gene_stats(G, dev)
+        X = eng.draw(rows, sc, 3, 11, gene_stats=fused)
+        eng.check()
+        want = count_stats(X)
+        for k in fused:
+            assert torch.equal(fused[k], want[k]), (G, n, depth, k)
+        assert torch.equal(X, eng.draw(rows, sc, 3, 11))               # the fused variant draws the same counts
+        X2 = eng.draw(rows, sc, 4, 11, gene_stats=fused)               # accumulators are added to
+        want2 = count_stats(X2)
+        for k in fused:
+            assert torch.equal(fused[k], want[k] + want2[k]), (G, n, depth, k, "second call")
+
+
 def test_count_stats_kernel_matches_numpy():
     from prosstt_b200.stats import count_stats, gene_mean_var
     rng = np.random.RandomState(6)
@@ -872,13 +931,17 @@ def test_full_size_config4_distribution_on_device():
     if torch.cuda.get_device_properties(0).total_memory < 120e9:
         pytest.skip("needs the 180 GB of a B200")
     from prosstt_b200.session import DensitySession
-    from prosstt_b200.stats import count_stats
+    from prosstt_b200.stats import count_stats, new_gene_stats
     t, alpha, beta = _bench_like_tree(7, 50, 10, 20000, seed=42)
     N = 1000000
     sess = DensitySession(t, alpha, beta, N, device=DEV)
-    sess.step(44)
+    fused = new_gene_stats(20000, DEV)
+    sess.step(44, gene_stats=fused)                                    # per-gene summaries fused into the draw
     sess.engine.check()
     st = count_stats(sess.X)
+    for k in ("gene_sum", "gene_sumsq", "gene_zeros"):                 # ... equal the second pass bit for bit
+        assert torch.equal(fused[k], st[k]), k
+    st.update(fused)
     M = sess.engine.means.double()                                     # (P, G)
     a = torch.from_numpy(alpha).to(DEV)
     b = torch.from_numpy(beta).to(DEV)

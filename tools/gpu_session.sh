@@ -1,6 +1,5 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s_pytest.txt
-bash tools/ab.sh atomic long longballot > gpurun_out/s_ab.txt 2>&1
-cat gpurun_out/s_pytest.txt gpurun_out/s_ab.txt
+for l in c64 c32 c16; do echo "== $l"; PST_LIB=tools/lib_$l.so python tools/stats_bench.py; done > gpurun_out/s_stats.txt 2>&1
+cat gpurun_out/s_stats.txt
