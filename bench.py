@@ -558,8 +558,7 @@ def run_e2e(a, tree, alpha, beta, sampler, dev, rank, world, barrier, max_over_r
         d2h = hX.numel() * width + ecells * (8 + 4 + 8) + listed * 12
         return float(ecells) * G * world * steps / dt, d2h, listed
 
-    v32, d2h, _ = run_pinned(torch.int32)                       # transport: library default for this host
-    v32d, _, _ = run_pinned(torch.int32, "direct") if world >= 4 else (v32, 0, 0)
+    v32, d2h, _ = run_pinned(torch.int32)                       # transport: the library default, "direct"
     v16, d2h16, listed = run_pinned(torch.uint16)
     v8, d2h8, listed8 = run_pinned(torch.uint8)
     # int32 host matrix, but the counts cross PCIe as uint8 + overflow list and host threads widen them
@@ -577,9 +576,6 @@ def run_e2e(a, tree, alpha, beta, sampler, dev, rank, world, barrier, max_over_r
             "note": "simulation.sample_density(tree, N, alpha, beta, host_out=pinned buffers): tree tables, "
                     "cdf and gene parameters uploaded per call; int32 counts + pseudotime + branch + "
                     "scalings land in host memory (chunked, copy overlapped with sampling)",
-            "int32_direct": {"value": v32d, "unit": UNIT,
-                             "note": "`value` with host_transport='direct' (int32 over PCIe, written by the copy engine); "
-                                     "the library default is 'direct' for up to 3 ranks per host and 'u8' above"},
             "default_api": default_api,
             "int32_via_u8": {"value": v32u8, "unit": UNIT, "host_threads_per_rank": threads, "host_cores": cores,
                              "d2h_bytes_per_step": int(d2h8),

@@ -276,6 +276,10 @@ int pst_store_fill(int32_t *out, int64_t n, int32_t value, void *stream);
  * 64 (signed).  threads <= 0 uses every hardware thread.  Returns 0, or -1 for an unsupported pair. */
 int pst_host_widen(const void *h_src, int32_t src_bits, void *h_dst, int32_t dst_bits, int64_t n,
                    int32_t threads);
+/* Advise transparent huge pages for a freshly allocated, still untouched result buffer (the fresh
+ * int64 array the reference-shaped call returns): first-touch page faults are what bounds the host
+ * expansion into pageable memory.  0 = advice given, 1 = not available; never an error. */
+int pst_host_prepare(void *h_buffer, int64_t bytes);
 /* h_dst[index[i] - base] = value[i] for base <= index[i] < base + n: writes the exact values of the
  * elements that saturated a narrow format (overflow list of pst_narrow_counts) into a widened chunk. */
 int pst_host_apply_overflow(void *h_dst, int32_t dst_bits, int64_t base, int64_t n,

@@ -118,10 +118,20 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   const uint4 w = philox_s(key0, key1, gene, c1, c2, 2u * (uint32_t)pa + 1u);
   float k;
   if (lam < 10.f) {                                // inversion, one uniform
-    const float u = u01(w.x);
-    float p = __expf(-lam), cdf = p;
-    k = 0.f;
-    while (u > cdf && k < 96.f) { k += 1.0f; p *= __fdividef(lam, k); cdf += p; }
+    if (w.x >= 0xFFF00000u) {
+      // top 2^-12 of the uniforms: fp32 cannot resolve the cdf next to 1 (and its uniform has 24 bits), so
+      // the far tail is inverted with 32 more random bits against a cdf accumulated in fp64
+      const double u = ((double)w.x + ((double)w.y + 0.5) * 2.3283064365386963e-10) * 2.3283064365386963e-10;
+      const double dl = (double)lam;
+      double p = exp(-dl), cdf = p, kk = 0.0;
+      while (u > cdf && kk < 1024.0) { kk += 1.0; p *= dl / kk; cdf += p; }
+      k = (float)kk;
+    } else {
+      const float u = u01(w.x);
+      float p = __expf(-lam), cdf = p;
+      k = 0.f;
+      while (u > cdf && k < 96.f) { k += 1.0f; p *= __fdividef(lam, k); cdf += p; }
+    }
   } else if (lam < 1.6e7f) {                       // PTRS (Hoermann 1993), two trials per block
     const float slam = lam * rsqrtf(lam), loglam = __logf(lam);
     const float b = fmaf(2.53f, slam, 0.931f);
@@ -169,7 +179,10 @@ constexpr int HY_KMAX = 2048;                // hard bound on inversion terms
 #define HY_STAGE2 24                         // unrolled terms at the start of the tail
 #endif
 constexpr float HY_MU_MAX = kInvMuMax, HY_VAR_MAX = kInvVarMax;   // route: mean <= 32 and sd <= 20 (nb_route_inversion)
-constexpr int HY_KFIX = 10;                                  // unrolled head terms
+#ifndef HY_KFIX_N
+#define HY_KFIX_N 10
+#endif
+constexpr int HY_KFIX = HY_KFIX_N;                           // unrolled head terms
 // mean <= 32 keeps P(0) >= e^-32 (|log2 P(0)| <= 46, t_k = P(k) k! inside the fp32 range)
 static_assert(HY_MU_MAX <= 32.0f, "the t_k form and the error bound of log2 P(0) assume mean <= 32");
 

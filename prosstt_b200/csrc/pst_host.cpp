@@ -7,6 +7,8 @@
 // Plain C ABI (include/prosstt_b200.h): host pointers, sizes, a thread count.
 #include <stdint.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -77,6 +79,23 @@ extern "C" int pst_host_widen(const void *src, int32_t src_bits, void *dst, int3
     return -1;
   }
   return 0;
+}
+
+// Ask for transparent huge pages under a freshly allocated (untouched) result buffer: the expansion
+// threads take one page fault per 2 MiB instead of one per 4 KiB when they first write it.  Advice only:
+// returns 0 when it was given, 1 when the platform does not offer it (nothing changes either way).
+extern "C" int pst_host_prepare(void *buffer, int64_t bytes) {
+#if defined(MADV_HUGEPAGE)
+  if (!buffer || bytes < (int64_t)(4 << 20)) return 1;
+  const uintptr_t huge = (uintptr_t)2 << 20;
+  const uintptr_t lo = ((uintptr_t)buffer + huge - 1) & ~(huge - 1);
+  const uintptr_t hi = ((uintptr_t)buffer + (uintptr_t)bytes) & ~(huge - 1);
+  if (hi <= lo) return 1;
+  return madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE) == 0 ? 0 : 1;
+#else
+  (void)buffer; (void)bytes;
+  return 1;
+#endif
 }
 
 // dst[index[i] - base] = value[i] for the entries with base <= index[i] < base + n (the exact values of

@@ -118,17 +118,18 @@ def choice_cdf(p):
 
 
 def _content_key(m):
-    """Cheap fingerprint of one branch's means for the device-table cache: buffer address, shape and
-    every 17th value (a stride coprime to any G that is not a multiple of 17 visits every row and every
-    gene column).  An in-place edit of a row, a column or the whole array of tree.means[b] - ordinary
-    NumPy usage in scripts written for the reference - changes it, unlike id(); after editing single
-    elements call tree.invalidate_device_cache()."""
+    """Cheap fingerprint of one branch's means for the device-table cache: buffer address, shape, the
+    first and last pseudotime rows and ~4096 values at a fixed stride.  An in-place edit of the whole
+    array, of a gene column (seen in the first row) or of a pseudotime row (>= G/stride samples fall in
+    it) - ordinary NumPy usage in scripts written for the reference - changes it, unlike id(); after
+    editing single elements call tree.invalidate_device_cache().  ~0.05 ms per branch."""
     if isinstance(m, torch.Tensor):
         return ("t", m.data_ptr(), tuple(m.shape), m._version)
     a = np.asarray(m)
     flat = a.reshape(-1)
-    step = 17 if (a.ndim < 2 or a.shape[-1] % 17) else 19
-    return (a.__array_interface__["data"][0], a.shape, flat[::step].tobytes())
+    step = max(1, flat.size // 4096) | 1
+    edge = (a[0].tobytes(), a[-1].tobytes()) if a.ndim >= 2 and a.shape[0] else ()
+    return (a.__array_interface__["data"][0], a.shape, flat[::step].tobytes()) + edge
 
 
 def means_table(tree, tables, dev):
@@ -200,20 +201,14 @@ _STAGING = {}
 
 
 def _shared_host_transport():
-    """Transport of an int32 pinned host matrix when nothing was asked for.  One GPU per host: "direct"
-    (the copy engine writes the matrix, PCIe-bound at ~14e9 counts/s).  Several ranks on one host
-    (torchrun's LOCAL_WORLD_SIZE >= 4) share the host's PCIe root / memory system - 8 B200s of one box
-    reach 93 GB/s together, 2.3e10 counts/s as int32 - so the counts cross as uint8 + overflow list and
-    each rank's share of the host cores widens them (measured: profiles/r02_host_bw_8gpu.txt).
-    PST_HOST_TRANSPORT=direct|i32|u16|u8 overrides."""
-    forced = os.environ.get("PST_HOST_TRANSPORT")
-    if forced:
-        return forced
-    try:
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
-    except ValueError:
-        local_world = 1
-    return "u8" if local_world >= 4 else "direct"
+    """Transport of an int32 pinned host matrix when nothing was asked for: "direct" (the copy engine
+    writes the matrix: 55-57 GB/s = 1.4e10 counts/s for one B200).  Measured on the 8-GPU box
+    (profiles/r02_host_bw_8gpu.txt): all eight ranks together get 98 GB/s of device->host copies and
+    88 GB/s of CPU writes - the HOST MEMORY system of the (virtualised, one NUMA node, 32 vCPU) box is the
+    limit, not the links - so sending uint8 and widening on the host (6 B of host traffic per count
+    instead of 4) is slower there (1.96e10 against 2.31e10 counts/s) and only the narrow formats kept
+    narrow in host memory go faster.  PST_HOST_TRANSPORT=direct|i32|u16|u8 overrides."""
+    return os.environ.get("PST_HOST_TRANSPORT") or "direct"
 
 
 def _pinned_staging(dev, nbytes):

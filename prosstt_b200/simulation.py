@@ -416,6 +416,7 @@ def _sample_counts(engine, rows, s32, seed, first, dtype, out):
     n = int(rows.numel())
     direct = want in (np.dtype(np.int32), np.dtype(np.int64))
     host = np.empty((n, engine.G), dtype=want if direct else np.int64)
+    nat.load().pst_host_prepare(host.ctypes.data, host.nbytes)       # huge pages under the fresh result
     if n and engine.G:
         engine.draw_to_host(rows, s32, seed, first, host)
     torch.cuda.current_stream(engine.dev).synchronize()

@@ -1280,6 +1280,26 @@ def test_inversion_far_tail_mass_is_pinned_from_both_sides():
         assert int(Xi.max().item()) <= k11, (m, a, b, int(Xi.max().item()), k11)
         # the body is untouched: mean within 5 sigma
         assert abs(Xi.double().mean().item() - m) < 5 * np.sqrt((a * m * m + b * m) / N)
+    # the mixture's small-lambda Poisson inversion has the same fp32 limit next to 1: its top 2^-12 uniforms
+    # are inverted in fp64 (round 2; the nearly-Poisson regime mu = 5 was 3.5 sigma light at 1e9 draws)
+    del X
+    regimes = [(5.0, 0.001, 1.05), (1.8, 0.2, 2.0)]
+    mu = np.repeat([r[0] for r in regimes], copies)
+    t = _flat_tree(mu)
+    eng = CountEngine(t, TreeTables(t, dev), np.repeat([r[1] for r in regimes], copies),
+                      np.repeat([r[2] for r in regimes], copies), dev, sampler="gamma_poisson")
+    X = eng.draw(torch.zeros(n, dtype=torch.int32, device=dev), torch.ones(n, dtype=torch.float32, device=dev), 4242, 0)
+    eng.check()
+    for i, (m, a, b) in enumerate(regimes):
+        theta = a * m + b - 1
+        r, p = m / theta, 1 / (1 + theta)
+        Xi = X[:, copies * i:copies * (i + 1)]
+        for level in (1e-6, 1e-7):
+            k = int(scipy.stats.nbinom.isf(level, r, p))
+            expect = scipy.stats.nbinom.sf(k, r, p) * N
+            seen = int((Xi > k).sum().item())
+            lo, hi = scipy.stats.poisson.ppf(1e-5, expect), scipy.stats.poisson.ppf(1 - 1e-5, expect)
+            assert lo <= seen <= hi, ("gamma_poisson", m, a, b, level, k, seen, expect)
 
 
 def test_sampler_parameterisation_f32_matches_get_pr_umi():

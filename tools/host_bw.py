@@ -60,8 +60,15 @@ for name, sb, db, cnt in (("u8->i32", 8, 32, n // 4), ("i32->i64", 32, 64, n // 
         t0 = time.perf_counter()
         lib.pst_host_widen(src.data_ptr(), sb, fresh.ctypes.data, db, cnt, threads)
         dtf = time.perf_counter() - t0
-        out.append("%s threads %2d: into pinned %.2f Gcounts/s (%.1f GB/s written); into fresh pageable %.2f Gcounts/s"
-                   % (name, threads, cnt / dt / 1e9, cnt * db / 8 / dt / 1e9, cnt / dtf / 1e9))
+        del fresh
+        fresh = np.empty(cnt * db // 8, dtype=np.uint8)
+        adv = lib.pst_host_prepare(fresh.ctypes.data, fresh.nbytes)
+        t0 = time.perf_counter()
+        lib.pst_host_widen(src.data_ptr(), sb, fresh.ctypes.data, db, cnt, threads)
+        dth = time.perf_counter() - t0
+        out.append("%s threads %2d: into pinned %.2f Gcounts/s (%.1f GB/s written); into fresh pageable %.2f Gcounts/s; "
+                   "with huge-page advice (rc %d) %.2f Gcounts/s"
+                   % (name, threads, cnt / dt / 1e9, cnt * db / 8 / dt / 1e9, cnt / dtf / 1e9, adv, cnt / dth / 1e9))
         del fresh
 for r in range(world):
     barrier()

@@ -57,7 +57,27 @@ for name in ("c2", "c5"):
         rec["oracle_s"] = nb * walk_s + (nb - 1) // 2 * pair_s
         rec["oracle_how"] = ("scaled: %d branches x %.2f s of walks + %d sibling pairs x %.1f s of per-gene pearsonr, one "
                              "attempt each (lower bound)" % (nb, walk_s, (nb - 1) // 2, pair_s))
-    rec["speedup"] = rec["oracle_s"] / rec["device_s"]
+    # the reference itself calls scipy.stats.pearsonr once per gene and sibling pair (sim_utils.py:145-168): timed
+    # here on 500 genes and scaled to G genes x sibling pairs (one attempt each) + one Python-level rvs call per
+    # walk step (simulation.py:114-121, ~30 us each: SURVEY.md section 6)
+    import scipy.stats
+    T = w["T"]
+    xa, xb = rng.normal(size=(T, 500)), rng.normal(size=(T, 500))
+    t0 = time.perf_counter()
+    for g in range(500):
+        scipy.stats.pearsonr(xa[:, g], xb[:, g])
+    per_gene = (time.perf_counter() - t0) / 500
+    nb = len(time_)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        scipy.stats.norm.rvs(loc=0, scale=0.1)
+    per_step = (time.perf_counter() - t0) / 2000
+    rec["reference_style_s"] = (nb - 1) // 2 * w["G"] * per_gene + nb * w["K"] * T * per_step
+    rec["reference_style_how"] = ("%d sibling pairs x %d genes x %.0f us per scipy.stats.pearsonr call + %d walk steps x %.0f us "
+                                  "per scipy rvs call, one attempt per branch (lower bound; the reference package is not "
+                                  "on the GPU box)" % ((nb - 1) // 2, w["G"], per_gene * 1e6, nb * w["K"] * T, per_step * 1e6))
+    rec["speedup_vs_oracle_port"] = rec["oracle_s"] / rec["device_s"]
+    rec["speedup_vs_reference_style"] = rec["reference_style_s"] / rec["device_s"]
     out[name] = rec
     print(name, json.dumps(rec), flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "lineage_bench.json"), "w"))

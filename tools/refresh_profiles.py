@@ -9,6 +9,7 @@ import sys
 
 rep, launches, bench_json = sys.argv[1:4]
 COUNTS = 4e9          # tools/sampler_bench.py --cells 200000 x 20000 genes
+TAG = "r02"
 WANT = """dram__bytes_read.sum dram__bytes_write.sum gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed gpu__time_duration.sum
 l1tex__t_sector_hit_rate.pct launch__block_size launch__grid_size launch__registers_per_thread launch__shared_mem_per_block_static
 lts__t_sector_hit_rate.pct sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active
@@ -22,17 +23,17 @@ smsp__thread_inst_executed_per_inst_executed.ratio""".split()
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 d = {h: (u, v) for h, u, v in zip(rows[0], rows[1], rows[2])}
-head = ("# ncu --set full, draw_counts_hybrid_kernel<10,1,0>, 200000 cells x 20000 genes (4e9 counts), final round-1 kernel "
-        "(tools/sampler_bench.py --cells 200000 --samplers hybrid)")
-with open("profiles/r01_draw_counts_hybrid_ncu_raw.txt", "w") as fh:
+head = ("# ncu --set full, draw_counts_kernel<10,true,false,false> (hybrid sampler), 200000 cells x 20000 genes (4e9 counts), "
+        "final round-2 kernel (tools/sampler_bench.py --cells 200000 --samplers hybrid)")
+with open("profiles/%s_draw_counts_ncu_raw.txt" % TAG, "w") as fh:
     fh.write(head + "\n" + "".join("%-95s %-12s %s\n" % (w, d[w][0], d[w][1]) for w in WANT if w in d))
 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
 rd = float(d["dram__bytes_read.sum"][1]) * scale[d["dram__bytes_read.sum"][0]]
 wr = float(d["dram__bytes_write.sum"][1]) * scale[d["dram__bytes_write.sum"][0]]
 json.dump({"bytes_per_count": round((rd + wr) / COUNTS, 3),
-           "source": "ncu --set full on draw_counts_hybrid_kernel<10,1,0>, 200000 cells x 20000 genes (4e9 counts), final round-1 "
+           "source": "ncu --set full on draw_counts_kernel (hybrid), 200000 cells x 20000 genes (4e9 counts), final round-2 "
                      "kernel: dram__bytes_read.sum %.3f GB + dram__bytes_write.sum %.3f GB "
-                     "(profiles/r01_draw_counts_hybrid_ncu_raw.txt)" % (rd / 1e9, wr / 1e9),
+                     "(profiles/%s_draw_counts_ncu_raw.txt)" % (rd / 1e9, wr / 1e9, TAG),
            "algorithmic_bytes_per_count": 4}, open("profiles/traffic.json", "w"))
 for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
           "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
@@ -72,9 +73,9 @@ headc, rest = collections.Counter(), collections.Counter()
 for r in data:
     e = num(r, "Instructions Executed")
     (headc if round(e) == H else rest)[opcode(r)] += e
-with open("profiles/r01_draw_counts_hybrid_sass_mix.txt", "w") as fh:
-    fh.write("# draw_counts_hybrid_kernel<10,1,0>, 200000 cells x 20000 genes (4e9 counts): executed SASS by opcode\n")
-    fh.write("# source: ncu --set full --import-source on (tools/sampler_bench.py --cells 200000 --samplers hybrid), final round-1 kernel\n")
+with open("profiles/%s_draw_counts_sass_mix.txt" % TAG, "w") as fh:
+    fh.write("# draw_counts_kernel (hybrid), 200000 cells x 20000 genes (4e9 counts): executed SASS by opcode\n")
+    fh.write("# source: ncu --set full --import-source on (tools/sampler_bench.py --cells 200000 --samplers hybrid), final round-2 kernel\n")
     fh.write("warp-instructions executed: %.4e  (%.2f per count, %.1f thread-instructions per count)\n" % (tot, tot / COUNTS, thr / COUNTS))
     fh.write("head iterations (one warp x one cell x 128 genes): %d ; warp-instructions per iteration: %.1f\n" % (H, tot / H))
     hs, rs = sum(headc.values()), sum(rest.values())
@@ -101,9 +102,19 @@ total = sum(agg.values())
 for k, v in agg.most_common(7):
     print("%-60s %8.3f ms %5.2f%% (%d)" % (k[:60], v, 100 * v / total, cnt[k]))
 print("total", total)
-open("profiles/r01_launches_bench_200k.csv", "w").write(open(launches).read())
+open("profiles/%s_launches_bench_200k.csv" % TAG, "w").write(open(launches).read())
 b = json.loads(open(bench_json).read().strip().splitlines()[-1])
-open("profiles/r01_bench_1gpu.json", "w").write(json.dumps(b) + "\n")
-print("bench: value %.4e  ms/step %.2f  roofline %.1f GB/s frac %.4f  e2e %.3e  u16 %.3e  u8 %.3e" % (
+open("profiles/%s_bench_c4_1gpu.json" % TAG, "w").write(json.dumps(b) + "\n")
+# speed of light of the instruction-bound kernel: issue slots of a B200 and the
+# instructions a perfectly adaptive sampler of this family would need
+winst = float(d["smsp__inst_executed.sum"][1]) / COUNTS
+json.dump({"issue_slots_per_s": 148 * 4 * 1.965e9, "warp_inst_per_count": round(winst, 3),
+           "thread_inst_per_count": round(thr / COUNTS, 1), "speed_of_light_warp_inst_per_count": round(57.5 / 32, 3),
+           "issue_utilisation": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"][1]) / 100,
+           "source": "148 SMs x 4 schedulers x 1.965 GHz issue slots; %.2f warp-instructions per count executed (ncu, "
+                     "profiles/%s_draw_counts_ncu_raw.txt); speed of light = 57.5 thread-instructions per count (Philox 13, "
+                     "parameterisation 14 + 4 MUFU, E[X]+1 = 4.5 cdf terms x 4, store and route 3; DESIGN.md 4.2)" % (winst, TAG)},
+          open("profiles/issue_bound.json", "w"))
+print("bench: value %.4e  ms/step %.2f  roofline %.1f GB/s frac %.4f  e2e %.3e  default_api %.3e  u16 %.3e  u8 %.3e" % (
     b["value"], b["ms_per_step"], b["roofline"]["achieved"], b["roofline"]["frac"], b["e2e"]["value"],
-    b["e2e"]["narrow_u16"]["value"], b["e2e"]["narrow_u8"]["value"]))
+    b["e2e"]["default_api"]["value"], b["e2e"]["narrow_u16"]["value"], b["e2e"]["narrow_u8"]["value"]))
