@@ -690,6 +690,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       if (ns >= 32 || ng >= 32) {
         while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
         while (ng >= 32) { ng -= 32; ng += drain_mixture(ng, 32); }
+        __syncwarp();                               // every lane has read the counters before lane 0 rewrites them
 #if HY_ENQ_ATOMIC
         if (lane == 0) wq.fill[0] = ns;
 #endif

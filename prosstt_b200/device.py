@@ -12,6 +12,23 @@ import torch
 from prosstt_b200 import _native as nat
 
 
+def tree_tables(tree, dev):
+    """TreeTables of `tree` on `dev`, cached on the tree: the integer maps depend only on the topology,
+    the branch lengths, the branch order and the root, which form the key - an edited tree gets new tables."""
+    try:
+        key = (str(dev), tuple((p, c) for p, c in tree.topology), tuple((b, int(tree.time[b])) for b in tree.branches),
+               tree.root)
+        hash(key)
+    except TypeError:
+        return TreeTables(tree, dev)
+    cache = tree.__dict__.setdefault("_tables_cache", {})
+    hit = cache.get(key)
+    if hit is None:
+        cache.clear()
+        hit = cache[key] = TreeTables(tree, dev)
+    return hit
+
+
 class TreeTables(object):
     """Integer maps of a tree flattened for the kernels (host numpy + device copies)."""
 

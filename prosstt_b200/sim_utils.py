@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from prosstt_b200 import _native as nat
-from prosstt_b200.device import TreeTables
+from prosstt_b200.device import TreeTables, tree_tables
 
 
 # ----------------------------------------------------------------------------- tree walking
@@ -144,7 +144,7 @@ def calc_relat_means(tree, programs, coefficients, device=None):
     """rel_means[b] = programs[b] . coefficients for every branch (sim_utils.py:190-213),
     one pst_rel_means launch over the packed tree."""
     dev = nat.device(device)
-    tables = TreeTables(tree, dev)
+    tables = tree_tables(tree, dev)
     H = nat.to_dev(coefficients, torch.float64, dev)
     K, G = H.shape
     W = torch.cat([nat.to_dev(np.asarray(programs[b]).reshape(-1, K), torch.float64, dev)
@@ -250,14 +250,15 @@ def pick_branches(tree, pseudotime, seed=None, first=0, device=None, uniforms=No
     zone-relative density index).  Names longer than the first branch name
     are NOT truncated (reference bug).  `uniforms` (one per cell) replaces
     the Philox stream - used to replay the reference's own draws."""
-    codes, _ = _pick_branch_codes(tree, pseudotime, seed, first, device, uniforms)
-    tables = TreeTables(tree, nat.device(device))
+    codes, _, flags = _pick_branch_codes(tree, pseudotime, seed, first, device, uniforms)
+    check_flags(flags)
+    tables = tree_tables(tree, nat.device(device))
     return tables.branch_names(codes.cpu().numpy())
 
 
 def _pick_branch_codes(tree, pseudotime, seed, first, device, uniforms=None, tables=None):
     dev = nat.device(device)
-    tables = tables or TreeTables(tree, dev)
+    tables = tables or tree_tables(tree, dev)
     st = nat.stream_ptr(dev)
     pt = pseudotime if isinstance(pseudotime, torch.Tensor) else \
         nat.to_dev(np.asarray(pseudotime), torch.int64, dev)
@@ -277,11 +278,17 @@ def _pick_branch_codes(tree, pseudotime, seed, first, device, uniforms=None, tab
              nat.ptr(tables.d("branch_start")), nat.ptr(tables.d("row_base")),
              nat.ptr(tables.d("T")), nat.ptr(dens), nat.ptr(codes), nat.ptr(rows),
              nat.ptr(flags), st)
+    # the status word is NOT read here (that would stall the stream in front of the count draw): the caller
+    # checks it with check_flags once the rest of its work has been queued
+    return codes, rows, flags
+
+
+def check_flags(flags):
+    """Read a device status word (one device->host sync) and raise what it reports."""
     from prosstt_b200.device import raise_flags
     word = int(flags.item())
     if word:
         raise_flags(word)
-    return codes, rows
 
 
 def pick_branch(tree, pseudotime, timezones=None, assignments=None, seed=None, device=None):

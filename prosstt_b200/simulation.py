@@ -28,7 +28,7 @@ import torch
 from prosstt_b200 import _native as nat
 from prosstt_b200 import count_model as cm
 from prosstt_b200 import sim_utils as sut
-from prosstt_b200.device import CountEngine, TreeTables, choice_cdf, raise_flags
+from prosstt_b200.device import CountEngine, TreeTables, choice_cdf, raise_flags, tree_tables
 from prosstt_b200.sharding import shard_range
 
 DEFAULT_SAMPLER = "hybrid"
@@ -118,7 +118,7 @@ class _LineageState(object):
 
     def __init__(self, tree, H, dev):
         self.dev = dev
-        self.tables = TreeTables(tree, dev)
+        self.tables = tree_tables(tree, dev)
         self.K, self.G = int(tree.modules), int(tree.G)
         self.H = nat.to_dev(H, torch.float64, dev)
         self.P = P = self.tables.P
@@ -476,7 +476,7 @@ def sample_density(tree, no_cells, alpha=0.3, beta=2, scale=True, scale_v=0.7, s
     (0 = all) together with their exact overflow list - the caller receives the same counts either way."""
     dev = nat.device(device)
     seed = nat.split_seed(seed)
-    tables = TreeTables(tree, dev)
+    tables = tree_tables(tree, dev)
     cdf = nat.to_dev(choice_cdf(tables.density_packed(tree)), torch.float64, dev)
     lo, hi = _shard_range(int(no_cells), shard)
     n = hi - lo
@@ -515,7 +515,7 @@ def sample_whole_tree(tree, n_factor, alpha=0.3, beta=2, scale=True, scale_mean=
     """Every tree position sampled n_factor times (simulation.py:474-517)."""
     dev = nat.device(device)
     seed = nat.split_seed(seed)
-    tables = TreeTables(tree, dev)
+    tables = tree_tables(tree, dev)
     total = len(tables.cover_pt) * int(n_factor)
     lo, hi = _shard_range(total, shard)
     n = hi - lo
@@ -593,17 +593,25 @@ def _sample_data_at_times(tree, sample_pt, branches=None, alpha=0.3, beta=2, sca
     cell (sharded callers)."""
     dev = nat.device(device)
     seed = nat.split_seed(seed)
-    tables = TreeTables(tree, dev)
+    tables = tree_tables(tree, dev)
     pt = sample_pt if isinstance(sample_pt, torch.Tensor) else \
         nat.to_dev(np.asarray(sample_pt), torch.int64, dev)
     n = int(pt.numel())
     if branches is None:
-        codes, rows = sut._pick_branch_codes(tree, pt, nat.derive_seed(seed, 0), _first, dev,
-                                             tables=tables)
+        codes, rows, flags = sut._pick_branch_codes(tree, pt, nat.derive_seed(seed, 0), _first, dev,
+                                                    tables=tables)
     else:
-        codes, rows = _rows_for(tables, pt, branches, dev)
-    return _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
-                           seed, _first, dev, dtype, out, sampler)
+        codes, rows, flags = _rows_for(tables, pt, branches, dev)
+    # a bad pseudotime / branch gives an out-of-range row, which the draw samples from row 0 and flags too;
+    # the index map's own status word is read after the draw has been queued (no stall in front of it)
+    try:
+        result = _draw_for_cells(tree, tables, pt, codes, rows, alpha, beta, scale, scale_mean, scale_v,
+                                 seed, _first, dev, dtype, out, sampler)
+    except IndexError:
+        sut.check_flags(flags)
+        raise
+    sut.check_flags(flags)
+    return result
 
 
 def _rows_for(tables, pt, branches, dev):
@@ -617,10 +625,7 @@ def _rows_for(tables, pt, branches, dev):
     nat.call("pst_rows_from_branch", nat.ptr(pt), nat.ptr(codes), n, tables.B,
              nat.ptr(tables.d("branch_start")), nat.ptr(tables.d("row_base")), nat.ptr(tables.d("T")),
              nat.ptr(rows), nat.ptr(flags), nat.stream_ptr(dev))
-    word = int(flags.item())
-    if word:
-        raise_flags(word)
-    return codes, rows
+    return codes, rows, flags
 
 
 def draw_counts(tree, pseudotime, branches, scalings, alpha, beta, seed=None, device=None,
@@ -630,10 +635,11 @@ def draw_counts(tree, pseudotime, branches, scalings, alpha, beta, seed=None, de
     variance = alpha_g mean^2 + beta_g mean)."""
     dev = nat.device(device)
     seed = nat.split_seed(seed)
-    tables = TreeTables(tree, dev)
+    tables = tree_tables(tree, dev)
     pt = pseudotime if isinstance(pseudotime, torch.Tensor) else \
         nat.to_dev(np.asarray(pseudotime), torch.int64, dev)
-    codes, rows = _rows_for(tables, pt, branches, dev)
+    codes, rows, flags = _rows_for(tables, pt, branches, dev)
+    sut.check_flags(flags)
     s32 = nat.to_dev(scalings, torch.float32, dev)
     if np.ndim(alpha) == 0:
         alpha = [alpha] * tree.G
