@@ -162,12 +162,20 @@ def launch_count():
 
 
 def to_dev(a, dtype, dev):
-    """Host array-like -> contiguous device tensor of the given torch dtype."""
+    """Host array-like -> contiguous device tensor of the given torch dtype.  The upload goes through a
+    pinned buffer of torch's caching host allocator and is asynchronous: a copy straight from pageable
+    memory would make the host wait for everything queued on the stream before it (the previous call's
+    draw kernel), which serialises host set-up and device work of back-to-back sampler calls."""
     if isinstance(a, torch.Tensor):
         return a.to(device=dev, dtype=dtype).contiguous()
     np_dtype = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32,
                 torch.int64: np.int64}[dtype]
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np_dtype))).to(dev)
+    host = np.ascontiguousarray(np.asarray(a, dtype=np_dtype))
+    if host.nbytes == 0 or host.nbytes > (256 << 20):
+        return torch.from_numpy(host).to(dev)
+    staged = torch.empty(host.shape, dtype=dtype, pin_memory=True)
+    staged.numpy()[...] = host
+    return staged.to(dev, non_blocking=True)
 
 
 def split_seed(seed):

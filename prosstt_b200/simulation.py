@@ -557,15 +557,18 @@ def sample_pseudotime_series(tree, cells, series_points, point_std, alpha=0.3, b
     max_time = tree.get_max_time()
     total = int(np.sum(cells))
     lo, hi = _shard_range(total, shard)
-    # per-cell loc/scale of the global cell range [lo, hi)
-    loc = np.repeat(np.asarray(series_points, dtype=np.float64), cells)[lo:hi]
-    std = np.repeat(np.asarray(point_std, dtype=np.float64), cells)[lo:hi]
+    # N(point, std) per cell of the global range [lo, hi): one launch per sample point over its own cells
+    # (element index = global cell index), no per-cell loc/scale arrays to build and upload
     n = hi - lo
     st = nat.stream_ptr(dev)
     z = torch.empty(n, dtype=torch.float64, device=dev)
-    nat.call("pst_normal_f64", nat.derive_seed(seed, 0), nat.TAG_SERIES_Z, lo, n, 0.0, 1.0,
-             nat.to_dev(loc, torch.float64, dev), nat.to_dev(std, torch.float64, dev),
-             nat.ptr(z), st)
+    start = 0
+    for point, count, std in zip(series_points, cells, point_std):
+        a, b = max(lo, start), min(hi, start + int(count))
+        if b > a:
+            nat.call("pst_normal_f64", nat.derive_seed(seed, 0), nat.TAG_SERIES_Z, a, b - a, float(point), float(std),
+                     None, None, z[a - lo:b - lo], st)
+        start += int(count)
     pt = torch.empty(n, dtype=torch.int64, device=dev)
     if n:
         nat.call("pst_times_from_normals", nat.ptr(z), n, int(max_time), nat.ptr(pt), st)
