@@ -32,3 +32,13 @@ import scipy.sparse  # noqa: E402
 back = scipy.sparse.load_npz(path)
 assert back.shape == tuple(Xd.shape) and back.nnz == int((Xd != 0).sum())
 print("logX", tuple(logX.shape), logX.dtype, "| csr nnz", back.nnz, "->", path)
+
+# per-gene summaries accumulated inside the draw (no second pass over the matrix)
+from prosstt_b200.session import DensitySession  # noqa: E402
+from prosstt_b200.stats import new_gene_stats  # noqa: E402
+sess = DensitySession(t, 0.2, 2.0, 10000)
+gs = new_gene_stats(t.G, sess.dev)
+sess.step(seed=7, gene_stats=gs)
+sess.engine.check()
+assert all(bool((gs[k] == count_stats(sess.X)[k]).all()) for k in gs)
+print("fused per-gene summaries: total counts", int(gs["gene_sum"].sum()), "zeros", int(gs["gene_zeros"].sum()))

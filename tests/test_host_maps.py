@@ -280,3 +280,43 @@ def test_epilogue_argument_checks_without_a_gpu():
         stats.transform_counts(cpu.float(), None, "log1p")
     with pytest.raises(TypeError):
         formats.widen(np.zeros((2, 2), dtype=np.int32), (np.array([]), np.array([])))
+
+
+def test_host_side_helpers_of_the_device_to_host_path():
+    """pst_host_widen / pst_host_apply_overflow / pst_host_checksum / pst_host_prepare are plain host code
+    (threads, no CUDA): every supported width pair, ragged sizes, thread counts, the overflow fix-up."""
+    import ctypes
+    lib = nat.load()
+    rng = np.random.RandomState(5)
+    for n in (0, 1, 63, 64, 1000003):
+        for sb, sdt, hi in ((8, np.uint8, 255), (16, np.uint16, 65535), (32, np.int32, 2 ** 31 - 1)):
+            src = rng.randint(0, hi + 1, size=n, dtype=np.int64).astype(sdt)
+            for db, ddt in ((32, np.int32), (64, np.int64)):
+                dst = np.full(n, -1, dtype=ddt)
+                for threads in (1, 3, 0):
+                    dst[:] = -1
+                    assert lib.pst_host_widen(src.ctypes.data, sb, dst.ctypes.data, db, n, threads) == 0
+                    assert np.array_equal(dst, src.astype(ddt)), (n, sb, db, threads)
+    assert lib.pst_host_widen(None, 8, None, 32, 5, 1) == -1
+    a = np.zeros(4, np.int32)
+    assert lib.pst_host_widen(a.ctypes.data, 32, a.ctypes.data, 16, 4, 1) == -1          # unsupported pair
+    # overflow list: entries inside [base, base + n) overwrite, the rest are skipped
+    dst = np.arange(10, dtype=np.int64)
+    idx = np.array([3, 12, 25, 19], dtype=np.int64)
+    val = np.array([300, 1200, 2500, 1900], dtype=np.int32)
+    assert lib.pst_host_apply_overflow(dst.ctypes.data, 64, 10, 10, idx.ctypes.data, val.ctypes.data, 4) == 0
+    assert dst.tolist() == [0, 1, 1200, 3, 4, 5, 6, 7, 8, 1900]
+    d32 = np.zeros(5, dtype=np.int32)
+    assert lib.pst_host_apply_overflow(d32.ctypes.data, 32, 0, 5, idx.ctypes.data, val.ctypes.data, 4) == 0
+    assert d32.tolist() == [0, 0, 0, 300, 0]
+    words = rng.randint(0, 2 ** 32, size=300001, dtype=np.uint64).astype(np.uint32)
+    lib.pst_host_checksum.restype = ctypes.c_uint64
+    for threads in (1, 4, 0):
+        assert lib.pst_host_checksum(words.ctypes.data, words.nbytes, threads) == int(words.astype(np.uint64).sum())
+    big = np.empty(8 << 20, dtype=np.uint8)
+    assert lib.pst_host_prepare(big.ctypes.data, big.nbytes) in (0, 1)                   # advice only
+    assert lib.pst_host_prepare(None, 0) == 1
+    lay = (ctypes.c_int64 * 6)()
+    assert lib.pst_draw_scratch_layout(1000, 400, 37, lay) == 0
+    assert lib.pst_draw_scratch_words(1000, 400, 37) == lay[4] + 4 * lay[5] and lay[4] % 4 == 0
+    assert lay[1] == 4 + 4 * lay[0] and lay[2] == lay[1] + 1000 and lay[3] == lay[2] + 38
