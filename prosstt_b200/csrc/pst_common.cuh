@@ -78,7 +78,7 @@ __device__ __forceinline__ float u01(uint32_t w) {
 }
 // The uniform of the NB cdf inversion, stretched to [0, 1 + 2^-15).  The fp32 pmf of the inversion
 // is exact up to a common factor 1 + eps (MUFU lg2/ex2/rcp and the rounding of log2 P(0); |eps| <=
-// 1.5e-5 for the parameters routed to the inversion, see nb_route_inversion), so its cdf tops out
+// 1.5e-5 for the parameters routed to the inversion, see nb_inversion_s_max), so its cdf tops out
 // anywhere in 1 +- 1.5e-5.  Stretching u by more than that makes the error one-sided: a u above the top
 // of the computed cdf is detected (in the tail path, invert_tail) and the count is redrawn,
 // so the accepted draws follow pmf (1+eps) renormalised, i.e. the exact pmf, and no part of the

@@ -3,26 +3,30 @@
 // scipy.stats.nbinom.rvs at simulation.py:647-648).
 //
 //   mu    = means[row_of_cell[n]][g] * scaling[n]
-//   theta = alpha[g]*mu + (beta[g]-1)          gamma scale   (scipy p = 1/(1+theta))
-//   r     = mu / theta                         gamma shape   (scipy n)
+//   theta = (alpha[g]*means[row][g]) * scaling[n] + (beta[g]-1)     gamma scale   (scipy p = 1/(1+theta))
+//   r     = mu / theta                                               gamma shape   (scipy n)
 //   X     ~ NB(r, 1/(1+theta))  ==  Poisson( theta * Gamma(r) )
 //
 // Work item = (cell, gene quad): one thread draws 4 neighbouring genes of one cell and
-// writes them with one 128-bit store; a warp writes 512 contiguous bytes of X.  Work is cut
-// into chunks (32 quads x 64 cells) that persistent warps claim from an atomic counter, so the
-// grid is load-balanced for any G and any mix of means.  Every uniform is a pure function of
-// (seed, cell, gene or gene quad, draw index) through Philox4x32-10, so counts do not depend
-// on launch shape, cell partition or GPU count.
+// writes them with one 128-bit store; a warp writes 512 contiguous bytes of X.  The cells are
+// visited grouped by tree row; work is cut into chunks (32 quads x at most 64 cells of ONE row)
+// that persistent warps claim from an atomic counter, so the grid is load-balanced for any G and
+// any mix of means.  Every uniform is a pure function of (seed, cell, gene or gene quad, draw
+// index) through Philox4x32-10, so counts do not depend on launch shape, visiting order, cell
+// partition or GPU count.
 //
-// Two samplers (both exact up to fp32 rounding, see DESIGN.md "sampler accuracy"), one kernel:
+// Two samplers (both exact up to the relative rounding of fp32 pmf terms, see DESIGN.md "sampler
+// accuracy"), one kernel:
 //   PST_SAMPLER_GAMMA_POISSON  every count by the mixture the way NumPy's legacy generator draws
 //                              it: Marsaglia-Tsang gamma, then Poisson by PTRS (lam >= 10) or
 //                              inversion (lam < 10)
 //   PST_SAMPLER_HYBRID         direct inversion of the NB cdf with ONE uniform for small means
-//                              (branch-free unrolled head + compacted tail), the mixture for
-//                              large means
+//                              (branch-free unrolled head + compacted tails; the top 2^-14 of the
+//                              uniforms finished by tail_fix_kernel with 64 bits against an fp64
+//                              cdf), the mixture for large means
 // In both, work that would make a warp diverge is pushed to per-warp shared-memory queues and
-// executed 32 entries at a time.
+// executed 32 entries at a time.  Optional (STATS): per-gene sum / sum of squares / zeros of the
+// counts, accumulated while the tile of X is still in L2.
 #include <stdlib.h>
 #include <algorithm>
 #include "pst_common.cuh"
@@ -152,24 +156,28 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
 // ---------------------------------------------------------------------------
 // kernel "hybrid": distribution-identical, divergence-aware, warp-autonomous.
 //
-// Small means (mu <= HY_MU_MAX = 32 and variance mu(1+theta) <= HY_VAR_MAX = 400): inversion of the NB
-//   cdf with one uniform u:  P(0) = (1+theta)^-r,  P(k+1) = P(k) (a + q k)/(k+1),
+// Small means (mean <= 32, variance <= 400, theta <= 32, shape <= 48 or theta < 0.1; decided per
+//   count as s <= s_max(M, alpha, beta-1), nb_inversion_s_max): inversion of the NB cdf with one
+//   uniform u:  P(0) = (1+theta)^-r,  P(k+1) = P(k) (a + q k)/(k+1),
 //   q = theta/(1+theta), a = q r,  X = #{k : u > cdf(k)}.
 //   Head: KFIX terms fully unrolled and branch-free for the 4 genes of a thread.  The state is
 //   t_k = P(k) k! and d_k = cdf(k) - u, so one term costs FFMA (a+qk), FMUL (t), FFMA
 //   (d += t/k!, 1/k! an immediate) and one integer op adding the sign bit of d to the count.
 //   The four uniforms of a thread come from ONE Philox block keyed (cell, gene quad).
 //   Tail: counts still undecided after KFIX terms (u above the cdf) are pushed to a per-warp
-//   shared-memory queue and finished 32 at a time with k warp-uniform (HY_STAGE2 more unrolled
-//   terms, then a generic loop with a vote every 4 terms), so the tail runs at full warp width
-//   whatever the mix of means.
-// Large means are pushed to a second per-warp queue and drawn 32 at a time by the mixture
+//   shared-memory queue and finished 32 at a time with k warp-uniform: HY_STAGE2 more unrolled
+//   terms; what is still open then moves to a queue of long searches, drained 32 at a time by a
+//   generic loop with a vote every 4 terms.  The tail runs at full warp width whatever the mix of means.
+//   Far tail: counts whose Philox word is in the top 2^-14 are listed and finished by
+//   tail_fix_kernel (64-bit uniform, fp64 cdf of the same fp32 terms, redraw above the cdf's top).
+// Large means are pushed to a third per-warp queue and drawn 32 at a time by the mixture
 //   (Marsaglia-Tsang + PTRS) on their own per-(cell, gene) Philox stream; the draw is a
 //   restartable step (mixture_step): rejected entries are re-queued, no warp spins in a loop.
 // The head writes the quad with one 128-bit store (a partial count in undecided and mixture
 //   slots); queue results overwrite them with 4-byte stores after a __syncwarp (same warp, ordered).
-// The route depends on the parameters only, never on the uniforms, so the draw is unbiased.
-// Work decomposition, prefetching and the dynamic chunk scheduler are described at the loop.
+// The inversion / mixture route depends on the parameters only, never on the uniforms, so the draw is
+//   unbiased; the far-tail route depends on the uniform alone and both sides invert the same cdf.
+// Work decomposition and the dynamic chunk scheduler are described at the kernel.
 // ---------------------------------------------------------------------------
 constexpr int HY_WARPS = 4;                  // warps per CTA
 constexpr int HY_THREADS = HY_WARPS * 32;
@@ -178,7 +186,7 @@ constexpr int HY_KMAX = 2048;                // hard bound on inversion terms
 #ifndef HY_STAGE2
 #define HY_STAGE2 24                         // unrolled terms at the start of the tail
 #endif
-constexpr float HY_MU_MAX = kInvMuMax, HY_VAR_MAX = kInvVarMax;   // route: mean <= 32 and sd <= 20 (nb_route_inversion)
+constexpr float HY_MU_MAX = kInvMuMax;                       // route: see nb_inversion_s_max
 #ifndef HY_KFIX_N
 #define HY_KFIX_N 10
 #endif
