@@ -26,7 +26,7 @@
 //                              cdf), the mixture for large means
 // In both, work that would make a warp diverge is pushed to per-warp shared-memory queues and
 // executed 32 entries at a time.  Optional (STATS): per-gene sum / sum of squares / zeros of the
-// counts, accumulated while the tile of X is still in L2.
+// counts, accumulated in registers from what the head stores and corrected by the drains.
 #include <stdlib.h>
 #include <algorithm>
 #include "pst_common.cuh"
@@ -305,9 +305,6 @@ struct HyWarpQueues {
 #define HY_MIX_ATOMIC 0   // mixture-queue slots: one atomic per lane (1) or ballots (0); measured equal at the bench
                           // depth, ballots better when every count takes the mixture (gamma_poisson sampler)
 #endif
-#ifndef HY_STAT_ROWS
-#define HY_STAT_ROWS 4    // rows of the chunk's tile in flight while the fused per-gene summaries are formed
-#endif
 #ifndef HY_CHUNK_CELLS
 #define HY_CHUNK_CELLS 64                    // most cells per chunk (x 32 quads = 8192 counts); all of one tree row
 #endif
@@ -323,8 +320,11 @@ struct HyWarpQueues {
 // atomic counter, so warps whose queues drain more often simply take fewer of them; consecutive
 // chunk ids are adjacent strips of the same cells (neighbouring warps complete the same X rows
 // together), and concurrently running warps share means rows in L2.
+#ifndef HY_STATS_CTAS
+#define HY_STATS_CTAS 7   // CTAs per SM of the instantiation with fused per-gene summaries
+#endif
 template <int KFIX, bool VEC, bool ALL_MIX, bool STATS>
-__global__ void __launch_bounds__(HY_THREADS, HY_MIN_CTAS)
+__global__ void __launch_bounds__(HY_THREADS, STATS ? HY_STATS_CTAS : HY_MIN_CTAS)
 draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, uint32_t G, uint32_t Q,
                    const float *__restrict__ scaling, const float *__restrict__ alpha,
                    const float *__restrict__ beta_m1, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx,
@@ -333,6 +333,16 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
                    uint32_t *__restrict__ tail, uint32_t tail_cap, unsigned long long *__restrict__ gene_sum,
                    unsigned long long *__restrict__ gene_sumsq, unsigned long long *__restrict__ gene_zeros) {
   __shared__ HyWarpQueues queues[HY_WARPS];
+  __shared__ unsigned int stat_lut[STATS ? 16 : 1];            // c -> [c == 0] | c << 7 | c^2 << 17, c <= KFIX
+  if constexpr (STATS) {
+    static_assert(KFIX <= 15 && KFIX * HY_CHUNK_CELLS < 1024 && KFIX * KFIX * HY_CHUNK_CELLS < 32768 &&
+                  HY_CHUNK_CELLS < 128, "packed per-gene accumulators");
+    if (threadIdx.x < 16) {
+      const unsigned c = threadIdx.x;
+      stat_lut[c] = (c == 0u ? 1u : 0u) | (c << 7) | ((c * c) << 17);
+    }
+    __syncthreads();
+  }
   HyWarpQueues &wq = queues[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -349,16 +359,13 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
   __syncwarp();
 
 
-  // Write a finished search.  With fused summaries (STATS) an entry whose chunk has already been summed
-  // carries bit 31 in its gene word: the sum saw the partial count KFIX there, the difference is added now.
+  // Write a finished search.  With fused summaries (STATS) the head has summed the partial count KFIX for
+  // this element: the difference is added now.
   auto finish_search = [&](int2 w, int cn) {
-    const uint32_t gene = (uint32_t)w.y & 0x7fffffffu;
-    X[(uint64_t)(uint32_t)w.x * ldx + gene] = cn;
+    X[(uint64_t)(uint32_t)w.x * ldx + (uint32_t)w.y] = cn;
     if constexpr (STATS) {
-      if (w.y < 0) {
-        atomicAdd(gene_sum + gene, (unsigned long long)(cn - KFIX));
-        atomicAdd(gene_sumsq + gene, (unsigned long long)cn * (unsigned long long)cn - (unsigned long long)(KFIX * KFIX));
-      }
+      atomicAdd(gene_sum + w.y, (unsigned long long)(cn - KFIX));
+      atomicAdd(gene_sumsq + w.y, (unsigned long long)cn * (unsigned long long)cn - (unsigned long long)(KFIX * KFIX));
     }
   };
   // the open-ended part of a search, 32 long searches at a time: P(k) form from k = HY_TAIL0, a + q k
@@ -440,8 +447,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
     int ga = 0;                                     // attempt | stage << 16 (stage 1: x holds lambda)
     if (act) { g = wq.ge[first + lane]; ga = wq.ga[first + lane]; }
     __syncwarp();                                   // every entry is read before slots are reused
-    const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w) & 0x7fffffff;
-    const bool summed = __float_as_int(g.w) < 0;    // STATS: the chunk was summed with 0 in this element
+    const int ccell = __float_as_int(g.z), gene = __float_as_int(g.w);
     const bool have_lambda = (ga >> 16) != 0;
     const int att = ga & 0xffff;
     int status = MIX_DONE;
@@ -459,7 +465,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         if (value > 2147483520.f) { val = 2147483647; flag |= PST_FLAG_CLAMPED; }
         X[(uint64_t)(uint32_t)ccell * ldx + (uint32_t)gene] = val;
         if constexpr (STATS) {
-          if (summed && val > 0) {
+          if (val > 0) {                                 // the head summed a zero for this element
             atomicAdd(gene_sum + gene, (unsigned long long)val);
             atomicAdd(gene_sumsq + gene, (unsigned long long)val * (unsigned long long)val);
             atomicAdd(gene_zeros + gene, ~0ull);             // minus one
@@ -495,6 +501,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
     const uint32_t quad = min(strip * 32u + (uint32_t)lane, Q - 1u);
     const bool lane_first = strip * 32u + (uint32_t)lane < Q;     // not one of the repeated edge lanes
     const uint32_t g0 = quad * 4u;
+    unsigned int acc[4] = {0u, 0u, 0u, 0u};             // STATS: packed per-gene accumulators of this chunk
     // per-(row, gene) constants of this lane's quad, once per chunk
     float m[4], c[4], bm[4], smax[4];
     {
@@ -651,9 +658,17 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       // drained, which always writes them (the __syncwarp below orders this store before the drain's)
       {
         int32_t *dst = X + ((uint64_t)(uint32_t)cell * ldx + g0);
-        if constexpr (STATS) {                      // the summation reads mixture slots before their drain: 0 there
+        if constexpr (STATS) {
+          // Per-gene summaries fused into the draw (the notebooks' X.sum(axis=0), per-gene variance and zero
+          // fraction; pst_count_stats as a second pass costs a quarter of the draw).  What the head stores is
+          // summed here: final counts 0..KFIX-1, the partial value KFIX for a queued search and 0 for a
+          // mixture or far-tail slot; the drains and tail_fix_kernel add the difference when the element
+          // becomes final.  c, c^2 and [c == 0] of at most HY_CHUNK_CELLS head values fit one 32-bit word.
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cnt[j] = small[j] ? cnt[j] : 0;
+          for (int j = 0; j < 4; ++j) {
+            cnt[j] = small[j] ? cnt[j] : 0;
+            acc[j] += stat_lut[cnt[j]];
+          }
         }
         if (VEC) {
           *reinterpret_cast<int4 *>(dst) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
@@ -709,56 +724,14 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       }
     }
     if constexpr (STATS) {
-      // Per-gene summaries fused into the draw (the notebooks' X.sum(axis=0), per-gene variance and zero
-      // fraction; pst_count_stats as a second pass costs a quarter of the draw).  The lane adds up its four
-      // genes over the chunk's tile of X (64 cells x 512 bytes, written by this warp and still in L2): one
-      // atomic per gene and chunk.  The few elements that are not final yet are corrected when they are:
-      // counts on the tail list by tail_fix_kernel, queued entries by their drain.
-      // (entries still queued are summed with their partial value - KFIX for a search, 0 for the mixture -
-      // and marked: their drain adds the difference, see finish_search / drain_mixture)
-      __syncwarp();
-      {
-        const int nl = *(volatile int *)&wq.fill[1];
-        for (int i = lane; i < ns; i += 32) wq.sw[i].y |= (int)0x80000000;
-        for (int i = lane; i < nl; i += 32) wq.lw[i].y |= (int)0x80000000;
-        for (int i = lane; i < ng; i += 32) wq.ge[i].w = __int_as_float(__float_as_int(wq.ge[i].w) | (int)0x80000000);
-      }
-      __syncwarp();
-      unsigned long long sq[4] = {0, 0, 0, 0}, sm[4] = {0, 0, 0, 0};
-      unsigned int nz[4] = {0, 0, 0, 0};                   // nonzero counts; zeros = cells - nz
-      for (int c0 = 0; c0 < n_cells; c0 += HY_STAT_ROWS) {
-        if ((c0 & 31) == 0) meta_cell = order[pos0 + (uint32_t)min(c0 + lane, n_cells - 1)];
-        unsigned int v[HY_STAT_ROWS][4];
-#pragma unroll
-        for (int i = 0; i < HY_STAT_ROWS; ++i) {            // row loads in flight
-          const int32_t cell = __shfl_sync(0xffffffffu, meta_cell, (c0 + i) & 31);
-          const int32_t *row = X + ((uint64_t)(uint32_t)cell * ldx + g0);
-          const bool in = c0 + i < n_cells;
-          if (VEC) {
-            const int4 x = in ? __ldcg(reinterpret_cast<const int4 *>(row)) : make_int4(0, 0, 0, 0);
-            v[i][0] = (unsigned)x.x; v[i][1] = (unsigned)x.y; v[i][2] = (unsigned)x.z; v[i][3] = (unsigned)x.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[i][j] = (in && g0 + j < G) ? (unsigned)__ldcg(row + j) : 0u;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < HY_STAT_ROWS; ++i) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {                     // rows past the group read as 0: nothing added
-            sm[j] += v[i][j];                                // one IMAD.WIDE each (64-bit accumulate)
-            sq[j] += (unsigned long long)v[i][j] * v[i][j];
-            nz[j] += min(v[i][j], 1u);
-          }
-        }
-      }
+      // flush the chunk's per-gene accumulators: zeros in bits 0-6, sum in bits 7-16, sum of squares above
       if (lane_first) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (VEC || g0 + j < G) {
-            atomicAdd(gene_sum + g0 + j, sm[j]);
-            atomicAdd(gene_sumsq + g0 + j, sq[j]);
-            atomicAdd(gene_zeros + g0 + j, (unsigned long long)((unsigned)n_cells - nz[j]));
+            atomicAdd(gene_zeros + g0 + j, (unsigned long long)(acc[j] & 0x7fu));
+            atomicAdd(gene_sum + g0 + j, (unsigned long long)((acc[j] >> 7) & 0x3ffu));
+            atomicAdd(gene_sumsq + g0 + j, (unsigned long long)(acc[j] >> 17));
           }
         }
       }
@@ -1135,7 +1108,7 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
 
   // ---- the draw: persistent CTAs of 4 warps, one wave; never more warps than chunks can exist
   const int64_t need = (L.max_groups * n_strips + HY_WARPS - 1) / HY_WARPS;
-  const int64_t cap = (int64_t)num_sm() * HY_MIN_CTAS;
+  const int64_t cap = (int64_t)num_sm() * (stats ? HY_STATS_CTAS : HY_MIN_CTAS);
   const unsigned hb = (unsigned)(need < cap ? need : cap);
   const uint32_t tail_cap = (uint32_t)L.tail_cap;
   typedef unsigned long long ull;
