@@ -543,6 +543,11 @@ def run_e2e(a, tree, alpha, beta, sampler, dev, rank, world, barrier, max_over_r
     hco = torch.empty(ecells, dtype=torch.int32).pin_memory()
     hsc = torch.empty(ecells, dtype=torch.float64).pin_memory()
 
+    from prosstt_b200.device import _shared_host_transport, _host_threads
+    threads = _host_threads()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    auto = _shared_host_transport(threads)                    # what the library picks on this host
+
     def run_pinned(x_dtype, transport=None):
         hX = torch.empty((ecells, G), dtype=x_dtype).pin_memory()
         overflow = {}
@@ -552,37 +557,38 @@ def run_e2e(a, tree, alpha, beta, sampler, dev, rank, world, barrier, max_over_r
                                       host_out=(hX, hpt, hco, hsc, overflow), host_transport=transport, **api_kwargs())
         dt = clock(api_call, steps)
         listed = len(overflow.get("index", ()))
-        from prosstt_b200.device import _shared_host_transport
-        eff = transport or _shared_host_transport()
-        width = {"u8": 1, "u16": 2}.get(eff, 4) if x_dtype == torch.int32 else hX.element_size()
-        d2h = hX.numel() * width + ecells * (8 + 4 + 8) + listed * 12
-        return float(ecells) * G * world * steps / dt, d2h, listed
+        return float(ecells) * G * world * steps / dt, hX.numel(), listed
 
-    v32, d2h, _ = run_pinned(torch.int32)                       # transport: the library default, "direct"
-    v16, d2h16, listed = run_pinned(torch.uint16)
-    v8, d2h8, listed8 = run_pinned(torch.uint8)
-    # int32 host matrix, but the counts cross PCIe as uint8 + overflow list and host threads widen them
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    threads = max(1, cores // max(1, world))
-    hX32 = torch.empty((ecells, G), dtype=torch.int32).pin_memory()
-
-    def via_u8(seed_):
-        return sim.sample_density(tree, ecells * world, seed=seed_, dtype=np.int32, host_out=(hX32, hpt, hco, hsc),
-                                  host_transport="u8", host_threads=threads, **api_kwargs())
-    dt = clock(via_u8, steps)
-    v32u8 = float(ecells) * G * world * steps / dt
+    meta = ecells * (8 + 4 + 8)
+    v16, n16, listed = run_pinned(torch.uint16)
+    v8, n8, listed8 = run_pinned(torch.uint8)
+    d2h16 = 2 * n16 + meta + listed * 12
+    d2h8 = n8 + meta + listed8 * 12
+    # int32 host matrix: copied as int32 by the copy engine ("direct"), or crossing PCIe as uint8 + overflow
+    # list and widened by host threads ("u8").  `value` is the call with NO transport argument (the library
+    # picks one of the two from a 64 MB trial of this host's expansion rate); both are reported.
+    by_transport = {}
+    for tr in ("direct", "u8"):
+        by_transport[tr] = run_pinned(torch.int32, tr)[0]
+    v32 = run_pinned(torch.int32)[0]                          # no transport argument
+    d2h = {"direct": 4 * n8 + meta, "u8": d2h8}[auto]
     return {"value": v32, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "cells_per_step_per_gpu": ecells, "steps": steps,
+            "cells_per_step_per_gpu": ecells, "steps": steps, "transport": auto,
+            "host_threads_per_rank": threads, "host_cores": cores,
             "note": "simulation.sample_density(tree, N, alpha, beta, host_out=pinned buffers): tree tables, "
                     "cdf and gene parameters uploaded per call; int32 counts + pseudotime + branch + "
-                    "scalings land in host memory (chunked, copy overlapped with sampling)",
+                    "scalings land in host memory (chunked, copy overlapped with sampling); no transport "
+                    "argument: the library chose `transport` for this host (device.py:_shared_host_transport)",
             "default_api": default_api,
-            "int32_via_u8": {"value": v32u8, "unit": UNIT, "host_threads_per_rank": threads, "host_cores": cores,
-                             "d2h_bytes_per_step": int(d2h8),
-                             "note": "same int32 pinned host matrix as `value`, but the counts cross PCIe as uint8 + "
-                                     "exact overflow list into pinned staging and host threads (pst_host_widen, "
-                                     "pst_host_apply_overflow) expand them: a quarter of the PCIe bytes, 4 B/count of "
-                                     "host-memory writes by the CPU instead of by DMA"},
+            "int32_direct": {"value": by_transport["direct"], "unit": UNIT, "d2h_bytes_per_step": int(4 * n8 + meta),
+                             "note": "host_transport='direct': the copy engine writes the int32 matrix, 4 B per "
+                                     "count over PCIe"},
+            "int32_via_u8": {"value": by_transport["u8"], "unit": UNIT, "d2h_bytes_per_step": int(d2h8),
+                             "note": "host_transport='u8': same int32 pinned host matrix, but the counts cross PCIe "
+                                     "as uint8 + exact overflow list into pinned staging and host threads "
+                                     "(pst_host_widen_stream: non-temporal stores; pst_host_apply_overflow) expand "
+                                     "them: a quarter of the PCIe bytes, 4 B/count of host-memory writes by the "
+                                     "CPU instead of by DMA"},
             "narrow_u16": {"value": v16, "unit": UNIT, "d2h_bytes_per_step": int(d2h16),
                            "overflow_entries_last_step": int(listed),
                            "note": "same call with a uint16 host matrix: min(count, 65535) plus an exact "

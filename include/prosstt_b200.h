@@ -276,6 +276,13 @@ int pst_store_fill(int32_t *out, int64_t n, int32_t value, void *stream);
  * 64 (signed).  threads <= 0 uses every hardware thread.  Returns 0, or -1 for an unsupported pair. */
 int pst_host_widen(const void *h_src, int32_t src_bits, void *h_dst, int32_t dst_bits, int64_t n,
                    int32_t threads);
+/* The same expansion with non-temporal 64-byte stores (AVX-512; ordinary stores elsewhere and on the
+ * unaligned edges; 32 -> 32 bits is a streaming copy): for a destination that is NOT in cache - a
+ * pinned or re-used result matrix - the lines are written without being read first, which halves the
+ * host-memory traffic of the expansion.  A freshly allocated (never touched) destination is better
+ * served by pst_host_widen: its pages are zeroed into the cache by the first-touch fault. */
+int pst_host_widen_stream(const void *h_src, int32_t src_bits, void *h_dst, int32_t dst_bits, int64_t n,
+                          int32_t threads);
 /* Advise transparent huge pages for a freshly allocated, still untouched result buffer (the fresh
  * int64 array the reference-shaped call returns): first-touch page faults are what bounds the host
  * expansion into pageable memory.  0 = advice given, 1 = not available; never an error. */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "pst_csr_fill": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "pst_store_fill": (C.c_int, [_p, _i64, _i32, _p]),
     "pst_host_widen": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32]),
+    "pst_host_widen_stream": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32]),
     "pst_host_prepare": (C.c_int, [_p, _i64]),
     "pst_host_apply_overflow": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _i64]),
     "pst_host_checksum": (_u64, [_p, _i64, _i32]),

@@ -217,15 +217,55 @@ _STAGE_BYTES = 256 << 20                      # one pinned staging buffer (two p
 _STAGING = {}
 
 
-def _shared_host_transport():
-    """Transport of an int32 pinned host matrix when nothing was asked for: "direct" (the copy engine
-    writes the matrix: 55-57 GB/s = 1.4e10 counts/s for one B200).  Measured on the 8-GPU box
-    (profiles/r02_host_bw_8gpu.txt): all eight ranks together get 98 GB/s of device->host copies and
-    88 GB/s of CPU writes - the HOST MEMORY system of the (virtualised, one NUMA node, 32 vCPU) box is the
-    limit, not the links - so sending uint8 and widening on the host (6 B of host traffic per count
-    instead of 4) is slower there (1.96e10 against 2.31e10 counts/s) and only the narrow formats kept
-    narrow in host memory go faster.  PST_HOST_TRANSPORT=direct|i32|u16|u8 overrides."""
-    return os.environ.get("PST_HOST_TRANSPORT") or "direct"
+_WIDEN_RATE = {}
+
+
+def _widen_rate(threads):
+    """uint8 -> int32 expansion rate of this host (counts/s) with `threads` threads and streaming stores,
+    from one 64 MB trial per process and thread count (about 10 ms)."""
+    rate = _WIDEN_RATE.get(threads)
+    if rate is None:
+        import time
+        n = 1 << 24
+        src = np.zeros(n, dtype=np.uint8)
+        dst = np.empty(n, dtype=np.int32)
+        lib = nat.load()
+        best = None
+        for _ in range(3):                              # the first pass also faults the pages in
+            t0 = time.perf_counter()
+            lib.pst_host_widen_stream(src.ctypes.data, 8, dst.ctypes.data, 32, n, int(threads))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        rate = _WIDEN_RATE[threads] = n / max(best, 1e-9)
+    return rate
+
+
+_PCIE_INT32_RATE = 1.4e10     # counts/s of a direct int32 copy into pinned memory (55-57 GB/s, one B200 on PCIe Gen5 x16)
+
+
+def _shared_host_transport(threads):
+    """Transport of an int32 pinned host matrix when nothing was asked for.  "direct": the copy engine
+    writes the matrix, 4 B per count over PCIe (55-57 GB/s = 1.4e10 counts/s for one B200).  "u8": the
+    counts cross as uint8 + exact overflow list (a quarter of the bytes) and host threads expand them with
+    streaming stores (pst_host_widen_stream) - faster whenever this rank's share of the host cores expands
+    well above the PCIe rate, which a 64 MB trial decides once per process (16 cores: ~2.5e10 counts/s).
+    With eight ranks on a 32-vCPU box each rank has 4 threads and the host MEMORY system is the limit
+    (profiles/r02_host_bw_8gpu.txt): the rule then keeps "direct".  PST_HOST_TRANSPORT=direct|i32|u16|u8
+    overrides."""
+    forced = os.environ.get("PST_HOST_TRANSPORT")
+    if forced:
+        return forced
+    return "u8" if _widen_rate(threads) >= 1.3 * _PCIE_INT32_RATE else "direct"
+
+
+def _host_threads():
+    """Host threads of this rank for the expansion: its share of the cores when several ranks share a host."""
+    try:
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        local_world = 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, cores // local_world)
 
 
 def _pinned_staging(dev, nbytes):
@@ -288,7 +328,7 @@ class CountEngine(object):
         return out
 
     def draw_to_host(self, rows, scaling32, seed, cell0, host_out, chunk_cells=None, overflow_cap=None,
-                     transport=None, threads=0):
+                     transport=None, threads=0, fresh=False):
         """Sample in cell chunks and stream them into `host_out`, an (n, G) CPU tensor or C-contiguous
         NumPy array: sampling of chunk i+1 overlaps the transfer (and host-side expansion) of chunk i.
 
@@ -303,7 +343,10 @@ class CountEngine(object):
           PCIe in the transport format into pinned staging buffers (cached per device) and host threads
           (pst_host_widen) expand it into host_out, the overflow list is applied at the end: the caller
           receives exact int32 / int64 counts.  This is the path of the reference-shaped call, which
-          returns a fresh (pageable) int64 array.  Default transport: "i32" for pageable targets."""
+          returns a fresh (pageable) int64 array.  Default transport: "i32" for pageable targets; for a
+          pinned int32 target the faster of "direct" and "u8" on this host (_shared_host_transport).
+          The expansion uses streaming stores (pst_host_widen_stream) unless `fresh` says that host_out was
+          just allocated and never touched (its pages are zeroed into the cache by the first-touch faults)."""
         n = int(rows.numel())
         is_np = isinstance(host_out, np.ndarray)
         if is_np:
@@ -318,23 +361,17 @@ class CountEngine(object):
             raise ValueError("host_out must be an int32, int64, uint16 or uint8 CPU matrix of shape (%d, %d)"
                              % (n, self.G))
         narrow_dst = hdt in (torch.uint16, torch.uint8)
+        if not threads:
+            threads = _host_threads()
         if transport is None and not is_np and hdt == torch.int32 and pinned:
-            transport = _shared_host_transport()
+            transport = _shared_host_transport(threads)
         if transport in (None, "direct") and not is_np and hdt != torch.int64 and \
                 (pinned or narrow_dst or transport == "direct"):
             return self._draw_to_host_direct(rows, scaling32, seed, cell0, host_out, chunk_cells, overflow_cap)
         if narrow_dst:
             raise ValueError("a uint16 / uint8 host matrix must be a CPU tensor and takes transport 'direct'")
-        if not threads:
-            # several ranks on one host: each takes its share of the cores
-            try:
-                local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            except ValueError:
-                local_world = 1
-            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            threads = max(1, cores // local_world)
         return self._draw_to_host_staged(rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
-                                         transport or "i32", threads)
+                                         transport or "i32", threads, fresh)
 
     def stream_chunks(self, rows, scaling32, seed, cell0, consume, transport="i32", chunk_cells=None,
                       overflow_cap=None):
@@ -407,7 +444,7 @@ class CountEngine(object):
         return ovf_index[:count].cpu(), ovf_value[:count].cpu()
 
     def _draw_to_host_staged(self, rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
-                             transport, threads):
+                             transport, threads, fresh=False):
         n, G = int(rows.numel()), self.G
         width = {"u8": 1, "u16": 2, "i32": 4}.get(transport)
         if width is None:
@@ -415,10 +452,11 @@ class CountEngine(object):
         dst_bits = 32 if hdt == torch.int32 else 64
         dst_ptr = host_out.ctypes.data if isinstance(host_out, np.ndarray) else host_out.data_ptr()
         lib = nat.load()
+        widen = lib.pst_host_widen if fresh else lib.pst_host_widen_stream
         self.overflow = None
 
         def expand(staged, lo, hi):
-            rc = lib.pst_host_widen(staged.data_ptr(), 8 * width, dst_ptr + lo * G * (dst_bits // 8), dst_bits,
+            rc = widen(staged.data_ptr(), 8 * width, dst_ptr + lo * G * (dst_bits // 8), dst_bits,
                                     (hi - lo) * G, int(threads))
             if rc != 0:
                 raise nat.NativeError("pst_host_widen failed")

@@ -424,7 +424,7 @@ def _sample_counts(engine, rows, s32, seed, first, dtype, out):
     host = np.empty((n, engine.G), dtype=want if direct else np.int64)
     nat.load().pst_host_prepare(host.ctypes.data, host.nbytes)       # huge pages under the fresh result
     if n and engine.G:
-        engine.draw_to_host(rows, s32, seed, first, host)
+        engine.draw_to_host(rows, s32, seed, first, host, fresh=True)     # untouched pages: ordinary stores
     torch.cuda.current_stream(engine.dev).synchronize()
     engine.check()
     return host if direct else host.astype(want)

@@ -297,7 +297,18 @@ def test_host_side_helpers_of_the_device_to_host_path():
                     dst[:] = -1
                     assert lib.pst_host_widen(src.ctypes.data, sb, dst.ctypes.data, db, n, threads) == 0
                     assert np.array_equal(dst, src.astype(ddt)), (n, sb, db, threads)
+                # streaming-store form: same result for any alignment of the destination, nothing written
+                # outside [0, n)
+                for off in (0, 1, 5):
+                    if n <= off:
+                        continue
+                    pad = np.full(n + 32, -7, dtype=ddt)
+                    assert lib.pst_host_widen_stream(src[off:].ctypes.data, sb, pad[off + 3:].ctypes.data, db,
+                                                     n - off, 3) == 0
+                    assert np.array_equal(pad[off + 3:n + 3], src[off:].astype(ddt)), (n, sb, db, off)
+                    assert (pad[:off + 3] == -7).all() and (pad[n + 3:] == -7).all()
     assert lib.pst_host_widen(None, 8, None, 32, 5, 1) == -1
+    assert lib.pst_host_widen_stream(None, 8, None, 32, 5, 1) == -1
     a = np.zeros(4, np.int32)
     assert lib.pst_host_widen(a.ctypes.data, 32, a.ctypes.data, 16, 4, 1) == -1          # unsupported pair
     # overflow list: entries inside [base, base + n) overwrite, the rest are skipped

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Host side of the device->host path on this box: pinned D2H rate (1 and 2 copy streams), and the rate of
-pst_host_widen (uint8 -> int32, int32 -> int64, int32 copy) into pinned and into fresh pageable memory for a
-few thread counts.  Run on every rank concurrently under torchrun to see the aggregate."""
+pst_host_widen / pst_host_widen_stream (uint8 -> int32, int32 -> int64, uint8 -> int64, int32 copy) into pinned
+and into fresh pageable memory for a few thread counts.  Run on every rank concurrently under torchrun to see the aggregate."""
 import os
 import sys
 import time
@@ -48,28 +48,29 @@ for streams in (1, 2):
     out.append("D2H pinned, %d stream(s): %.1f GB/s" % (streams, 6 * nbytes / dt / 1e9))
 src = h[0]
 n = nbytes
-for name, sb, db, cnt in (("u8->i32", 8, 32, n // 4), ("i32->i64", 32, 64, n // 8), ("i32->i32", 32, 32, n // 4)):
+for name, sb, db, cnt in (("u8->i32", 8, 32, n // 4), ("i32->i64", 32, 64, n // 8), ("u8->i64", 8, 64, n // 8),
+                          ("i32->i32", 32, 32, n // 4)):
     dst_pinned = h[1]
-    for threads in sorted(set([1, 2, 4, 8, max(1, cores // max(1, world)), cores])):
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            lib.pst_host_widen(src.data_ptr(), sb, dst_pinned.data_ptr(), db, cnt, threads)
-        dt = (time.perf_counter() - t0) / 3
-        fresh = np.empty(cnt * db // 8, dtype=np.uint8)
-        t0 = time.perf_counter()
-        lib.pst_host_widen(src.data_ptr(), sb, fresh.ctypes.data, db, cnt, threads)
-        dtf = time.perf_counter() - t0
-        del fresh
-        fresh = np.empty(cnt * db // 8, dtype=np.uint8)
-        adv = lib.pst_host_prepare(fresh.ctypes.data, fresh.nbytes)
-        t0 = time.perf_counter()
-        lib.pst_host_widen(src.data_ptr(), sb, fresh.ctypes.data, db, cnt, threads)
-        dth = time.perf_counter() - t0
-        out.append("%s threads %2d: into pinned %.2f Gcounts/s (%.1f GB/s written); into fresh pageable %.2f Gcounts/s; "
-                   "with huge-page advice (rc %d) %.2f Gcounts/s"
-                   % (name, threads, cnt / dt / 1e9, cnt * db / 8 / dt / 1e9, cnt / dtf / 1e9, adv, cnt / dth / 1e9))
-        del fresh
+    for threads in sorted(set([1, 4, 8, max(1, cores // max(1, world)), cores])):
+        line = "%s threads %2d:" % (name, threads)
+        for label, fn in (("plain", lib.pst_host_widen), ("stream", lib.pst_host_widen_stream)):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn(src.data_ptr(), sb, dst_pinned.data_ptr(), db, cnt, threads)
+            dt = (time.perf_counter() - t0) / 3
+            rates = []
+            for advise in (False, True):
+                fresh = np.empty(cnt * db // 8, dtype=np.uint8)
+                if advise:
+                    lib.pst_host_prepare(fresh.ctypes.data, fresh.nbytes)
+                t0 = time.perf_counter()
+                fn(src.data_ptr(), sb, fresh.ctypes.data, db, cnt, threads)
+                rates.append(cnt / (time.perf_counter() - t0) / 1e9)
+                del fresh
+            line += "  %s: pinned %.2f Gcounts/s (%.1f GB/s written), fresh %.2f, fresh+hugepage advice %.2f;" % (
+                label, cnt / dt / 1e9, cnt * db / 8 / dt / 1e9, rates[0], rates[1])
+        out.append(line)
 for r in range(world):
     barrier()
     if r == rank:
