@@ -80,6 +80,39 @@ __device__ __forceinline__ bool ptrs_trial(float lam, float loglam, float a, flo
   return __logf(V) + log_inv_alpha - __logf(fmaf(a * ius, ius, b)) <= bound;
 }
 
+// One Marsaglia-Tsang attempt at lambda = theta Gamma(r), r = mu/theta (r < 1: Gamma(r) = Gamma(r+1) U^(1/r)),
+// from one Philox block: normal (Box-Muller, cosine branch) from w.x, w.y, acceptance uniform w.z, boost w.w.
+// Returns false when the attempt is rejected (never with `force`).
+__device__ __forceinline__ bool gamma_attempt(float mu, float theta, uint4 w, bool force, float &lam) {
+  const float r = __fdividef(mu, theta);
+  const bool lt1 = r < 1.0f;
+  const float shape = lt1 ? r + 1.0f : r;
+  const float d = shape - 0.3333333333f;
+  const float c = rsqrtf(9.0f * d);
+  const float rad2 = -2.0f * __logf(u01(w.x));                    // Box-Muller, cosine branch
+  const float xn = rad2 * rsqrtf(fmaxf(rad2, 1e-30f)) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
+  const float e = c * xn;
+  const float t = 1.0f + e;
+  const float v = t * t * t;
+  const float u = u01(w.z);
+  const float x2 = xn * xn;
+  bool ok = t > 0.f;
+  if (ok && !(u < 1.0f - 0.0331f * x2 * x2)) {
+    float h;
+    if (fabsf(e) < 0.1f) {
+      const float e2 = e * e;
+      h = d * e2 * e2 * (-0.75f + e * (0.6f + e * (-0.5f + e * (0.4285714286f + e * (-0.375f + e * 0.3333333333f)))));
+    } else {
+      h = 0.5f * x2 + d * (1.0f - v + __logf(v));
+    }
+    ok = __logf(u) < h;
+  }
+  if (!ok && !force) return false;
+  const float boost = lt1 ? __expf(__fdividef(__logf(u01(w.w)), r)) : 1.0f;   // Gamma(r) = Gamma(r+1) U^(1/r)
+  lam = theta * d * fmaxf(v, 0.f) * boost;
+  return true;
+}
+
 __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_lambda, int attempt,
                                                uint32_t key0, uint32_t key1, uint32_t gene, int64_t cell) {
   const uint32_t c1 = (uint32_t)cell, c2 = (TAG_COUNT << 16) | (uint32_t)((uint64_t)cell >> 32);
@@ -87,34 +120,8 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
   float lam;
   int pa = attempt;                                // Poisson attempt index
   if (!have_lambda) {                              // x = mu: gamma stage
-    const float mu = x;
-    const float r = __fdividef(mu, theta);
-    const bool lt1 = r < 1.0f;
-    const float shape = lt1 ? r + 1.0f : r;
     const uint4 w = philox_s(key0, key1, gene, c1, c2, 2u * (uint32_t)attempt);
-    const float d = shape - 0.3333333333f;
-    const float c = rsqrtf(9.0f * d);
-    const float rad2 = -2.0f * __logf(u01(w.x));                    // Box-Muller, cosine branch
-    const float xn = rad2 * rsqrtf(fmaxf(rad2, 1e-30f)) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
-    const float e = c * xn;
-    const float t = 1.0f + e;
-    const float v = t * t * t;
-    const float u = u01(w.z);
-    const float x2 = xn * xn;
-    bool ok = t > 0.f;
-    if (ok && !(u < 1.0f - 0.0331f * x2 * x2)) {
-      float h;
-      if (fabsf(e) < 0.1f) {
-        const float e2 = e * e;
-        h = d * e2 * e2 * (-0.75f + e * (0.6f + e * (-0.5f + e * (0.4285714286f + e * (-0.375f + e * 0.3333333333f)))));
-      } else {
-        h = 0.5f * x2 + d * (1.0f - v + __logf(v));
-      }
-      ok = __logf(u) < h;
-    }
-    if (!ok && !force) return MixResult{0.f, MIX_RETRY_GAMMA};
-    const float boost = lt1 ? __expf(__fdividef(__logf(u01(w.w)), r)) : 1.0f;   // Gamma(r) = Gamma(r+1) U^(1/r)
-    lam = theta * d * fmaxf(v, 0.f) * boost;
+    if (!gamma_attempt(x, theta, w, force, lam)) return MixResult{0.f, MIX_RETRY_GAMMA};
     pa = 0;
   } else {
     lam = x;                                       // gamma already accepted
