@@ -109,6 +109,13 @@ __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ft
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_fast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// natural log / exp / quotient on those: what __logf, __expf and __fdividef compute for normal arguments,
+// without their subnormal-argument fix-ups (3-4 extra instructions each); every caller's arguments are
+// normal numbers or may be flushed to zero
+__device__ __forceinline__ float log_fast(float x) { return lg2_fast(x) * 0.6931471806f; }
+__device__ __forceinline__ float exp_fast(float x) { return ex2_fast(x * 1.4426950409f); }
+__device__ __forceinline__ float div_fast(float a, float b) { return a * rcp_fast(b); }
 
 // ---------------------------------------------------------------------------
 // NB parameterisation of the inversion path, fp32 (count_model.py:156-161 in the gamma-Poisson

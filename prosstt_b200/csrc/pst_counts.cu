@@ -16,17 +16,18 @@
 // partition or GPU count.
 //
 // Two samplers (both exact up to the relative rounding of fp32 pmf terms, see DESIGN.md "sampler
-// accuracy"), one kernel:
-//   PST_SAMPLER_GAMMA_POISSON  every count by the mixture the way NumPy's legacy generator draws
-//                              it: Marsaglia-Tsang gamma, then Poisson by PTRS (lam >= 10) or
-//                              inversion (lam < 10)
-//   PST_SAMPLER_HYBRID         direct inversion of the NB cdf with ONE uniform for small means
-//                              (branch-free unrolled head + compacted tails; the top 2^-14 of the
-//                              uniforms finished by tail_fix_kernel with 64 bits against an fp64
+// accuracy"), two kernels with the same work decomposition:
+//   PST_SAMPLER_GAMMA_POISSON  draw_counts_mixture_kernel: every count by the mixture the way NumPy's
+//                              legacy generator draws it - Marsaglia-Tsang gamma, then Poisson by PTRS
+//                              (lam >= 10) or inversion (lam < 10) - as a pipeline of per-warp queues,
+//                              one per stage, so that each stage runs 32 entries wide
+//   PST_SAMPLER_HYBRID         draw_counts_kernel: direct inversion of the NB cdf with ONE uniform for
+//                              small means (branch-free unrolled head + compacted tails; the top 2^-14
+//                              of the uniforms finished by tail_fix_kernel with 64 bits against an fp64
 //                              cdf), the mixture for large means
 // In both, work that would make a warp diverge is pushed to per-warp shared-memory queues and
 // executed 32 entries at a time.  Optional (STATS): per-gene sum / sum of squares / zeros of the
-// counts, accumulated in registers from what the head stores and corrected by the drains.
+// counts (hybrid: accumulated in registers from what the head stores and corrected by the drains).
 #include <stdlib.h>
 #include <algorithm>
 #include "pst_common.cuh"
@@ -75,22 +76,22 @@ __device__ __forceinline__ bool ptrs_trial(float lam, float loglam, float a, flo
     } else {
       l1 = log1pf(y) - y;
     }
-    bound = k * l1 - 0.5f * __logf(6.2831853072f * k) - ik * (0.0833333333f - 0.0027777778f * ik * ik);
+    bound = k * l1 - 0.5f * log_fast(6.2831853072f * k) - ik * (0.0833333333f - 0.0027777778f * ik * ik);
   }
-  return __logf(V) + log_inv_alpha - __logf(fmaf(a * ius, ius, b)) <= bound;
+  return log_fast(V) + log_inv_alpha - log_fast(fmaf(a * ius, ius, b)) <= bound;
 }
 
 // One Marsaglia-Tsang attempt at lambda = theta Gamma(r), r = mu/theta (r < 1: Gamma(r) = Gamma(r+1) U^(1/r)),
 // from one Philox block: normal (Box-Muller, cosine branch) from w.x, w.y, acceptance uniform w.z, boost w.w.
 // Returns false when the attempt is rejected (never with `force`).
 __device__ __forceinline__ bool gamma_attempt(float mu, float theta, uint4 w, bool force, float &lam) {
-  const float r = __fdividef(mu, theta);
+  const float r = div_fast(mu, theta);
   const bool lt1 = r < 1.0f;
   const float shape = lt1 ? r + 1.0f : r;
   const float d = shape - 0.3333333333f;
-  const float c = rsqrtf(9.0f * d);
-  const float rad2 = -2.0f * __logf(u01(w.x));                    // Box-Muller, cosine branch
-  const float xn = rad2 * rsqrtf(fmaxf(rad2, 1e-30f)) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
+  const float c = rsqrt_fast(9.0f * d);
+  const float rad2 = -2.0f * log_fast(u01(w.x));                    // Box-Muller, cosine branch
+  const float xn = rad2 * rsqrt_fast(fmaxf(rad2, 1e-30f)) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
   const float e = c * xn;
   const float t = 1.0f + e;
   const float v = t * t * t;
@@ -103,14 +104,40 @@ __device__ __forceinline__ bool gamma_attempt(float mu, float theta, uint4 w, bo
       const float e2 = e * e;
       h = d * e2 * e2 * (-0.75f + e * (0.6f + e * (-0.5f + e * (0.4285714286f + e * (-0.375f + e * 0.3333333333f)))));
     } else {
-      h = 0.5f * x2 + d * (1.0f - v + __logf(v));
+      h = 0.5f * x2 + d * (1.0f - v + log_fast(v));
     }
-    ok = __logf(u) < h;
+    ok = log_fast(u) < h;
   }
   if (!ok && !force) return false;
-  const float boost = lt1 ? __expf(__fdividef(__logf(u01(w.w)), r)) : 1.0f;   // Gamma(r) = Gamma(r+1) U^(1/r)
+  const float boost = lt1 ? exp_fast(div_fast(log_fast(u01(w.w)), r)) : 1.0f;   // Gamma(r) = Gamma(r+1) U^(1/r)
   lam = theta * d * fmaxf(v, 0.f) * boost;
   return true;
+}
+
+// The same attempt without branches (same arithmetic on the path each lane would have taken, same result):
+// in a full warp the squeeze almost never spares every lane the logarithms, and four of these back to
+// back (the quad of a lane in the gamma_poisson kernel) interleave their Philox and MUFU latencies.
+__device__ __forceinline__ bool gamma_attempt_dense(float mu, float theta, uint4 w, bool force, float &lam) {
+  const float r = div_fast(mu, theta);
+  const bool lt1 = r < 1.0f;
+  const float shape = lt1 ? r + 1.0f : r;
+  const float d = shape - 0.3333333333f;
+  const float c = rsqrt_fast(9.0f * d);
+  const float rad2 = -2.0f * log_fast(u01(w.x));
+  const float xn = rad2 * rsqrt_fast(fmaxf(rad2, 1e-30f)) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f);
+  const float e = c * xn;
+  const float t = 1.0f + e;
+  const float v = t * t * t;
+  const float u = u01(w.z);
+  const float x2 = xn * xn;
+  const float e2 = e * e;
+  const float h_series = d * e2 * e2 * (-0.75f + e * (0.6f + e * (-0.5f + e * (0.4285714286f + e * (-0.375f + e * 0.3333333333f)))));
+  const float h_log = 0.5f * x2 + d * (1.0f - v + log_fast(v));
+  const float h = fabsf(e) < 0.1f ? h_series : h_log;
+  const bool ok = (t > 0.f) && ((u < 1.0f - 0.0331f * x2 * x2) || (log_fast(u) < h));
+  const float boost = lt1 ? exp_fast(div_fast(log_fast(u01(w.w)), r)) : 1.0f;
+  lam = theta * d * fmaxf(v, 0.f) * boost;
+  return ok || force;
 }
 
 __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_lambda, int attempt,
@@ -139,22 +166,22 @@ __device__ __noinline__ MixResult mixture_step(float x, float theta, bool have_l
       k = (float)kk;
     } else {
       const float u = u01(w.x);
-      float p = __expf(-lam), cdf = p;
+      float p = exp_fast(-lam), cdf = p;
       k = 0.f;
-      while (u > cdf && k < 96.f) { k += 1.0f; p *= __fdividef(lam, k); cdf += p; }
+      while (u > cdf && k < 96.f) { k += 1.0f; p *= div_fast(lam, k); cdf += p; }
     }
   } else if (lam < 1.6e7f) {                       // PTRS (Hoermann 1993), two trials per block
-    const float slam = lam * rsqrtf(lam), loglam = __logf(lam);
+    const float slam = lam * rsqrt_fast(lam), loglam = log_fast(lam);
     const float b = fmaf(2.53f, slam, 0.931f);
     const float a = fmaf(0.02483f, b, -0.059f);
-    const float log_inv_alpha = __logf(1.1239f + __fdividef(1.1328f, b - 3.4f));
-    const float vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
+    const float log_inv_alpha = log_fast(1.1239f + div_fast(1.1328f, b - 3.4f));
+    const float vr = 0.9277f - div_fast(3.6224f, b - 2.0f);
     bool ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.x) - 0.5f, u01(w.y), k);
     if (!ok) ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.z) - 0.5f, u01(w.w), k);
     if (!ok && !force) return MixResult{lam, MIX_RETRY_POISSON};
     k = fmaxf(k, 0.f);
   } else {                                         // beyond 2^24: normal limit (TV error < 1e-4)
-    k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * __logf(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));   // never hot
+    k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * log_fast(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));   // never hot
   }
   return MixResult{k, MIX_DONE};
 }
@@ -330,7 +357,7 @@ struct HyWarpQueues {
 #ifndef HY_STATS_CTAS
 #define HY_STATS_CTAS 7   // CTAs per SM of the instantiation with fused per-gene summaries
 #endif
-template <int KFIX, bool VEC, bool ALL_MIX, bool STATS>
+template <int KFIX, bool VEC, bool STATS>
 __global__ void __launch_bounds__(HY_THREADS, STATS ? HY_STATS_CTAS : HY_MIN_CTAS)
 draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restrict__ means, uint32_t G, uint32_t Q,
                    const float *__restrict__ scaling, const float *__restrict__ alpha,
@@ -533,7 +560,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         c[j] = al[j] * m[j];
-        smax[j] = ALL_MIX ? -1.f : nb_inversion_s_max(m[j], al[j], bm[j]);
+        smax[j] = nb_inversion_s_max(m[j], al[j], bm[j]);
       }
     }
     // theta = c s + (beta-1) >= beta-1 on the inversion route, so the Poisson-limit series below can only
@@ -568,11 +595,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         th[j] = fmaf(c[j], s, bm[j]);
         small[j] = s <= smax[j];                    // the inversion's route (false on NaN)
       }
-      if constexpr (ALL_MIX) {
-        // "gamma_poisson" sampler: every count is drawn by the mixture (through the same queue)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { t[j] = 0.f; d[j] = 0.f; a[j] = 0.f; q[j] = 0.f; cnt[j] = 0; }
-      } else {
+      {
         float e2[4];
         const int64_t gcell = cell0 + cell;
         const uint4 rnd = philox(key, quad, (uint32_t)gcell,
@@ -615,7 +638,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       }
       // large means: queue them for the mixture now, so mu/theta are dead during the head.  Many
       // (cell, strip) pairs have none: one vote skips the block
-      if (ALL_MIX || __any_sync(0xffffffffu, !(small[0] && small[1] && small[2] && small[3]))) {
+      if (__any_sync(0xffffffffu, !(small[0] && small[1] && small[2] && small[3]))) {
 #if HY_MIX_ATOMIC
         // a lane reserves the slots of its (up to four) entries with one shared-memory atomic
         bool tm[4];
@@ -650,7 +673,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
 #endif
       }
       // head of the inversion: terms 1..KFIX-1, branch-free, k compile-time
-      if constexpr (!ALL_MIX) {
+      {
 #pragma unroll
         for (int k = 0; k < KFIX - 1; ++k) {
 #pragma unroll
@@ -686,7 +709,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         }
       }
       // enqueue the undecided inversions
-      if constexpr (!ALL_MIX) {
+      {
 #if HY_ENQ_ATOMIC
         // slots come from a shared-memory counter
 #pragma unroll
@@ -714,8 +737,6 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
         }
         __syncwarp();
 #endif
-      } else {
-        __syncwarp();
       }
       if (ns >= 32 || ng >= 32) {
         while (ns >= 32) { ns -= 32; drain_search(ns, 32); }
@@ -754,6 +775,322 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
   if (flag) atomicOr(flags, flag);
   // the last warp to leave rearms the scheduler words for the next launch
   if (lane == 0) {
+    const unsigned done = atomicAdd(&g_sched[sched][1], 1u);
+    if (done == (unsigned)n_warps - 1u) { g_sched[sched][0] = 0u; g_sched[sched][1] = 0u; __threadfence(); }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernel "gamma_poisson": every count by the mixture NumPy's legacy generator draws it from
+// (Marsaglia-Tsang gamma, then Poisson by inversion below lambda = 10 and by PTRS above), organised as
+// a pipeline of three per-warp queues so that every stage runs 32 entries wide:
+//   gamma stage     attempt 0 of a count runs straight from the registers of the lane that owns it (all
+//                   32 lanes, no queue); an accepted lambda is routed by its size to one of the two
+//                   Poisson queues, a rejected attempt (~5 %) goes to the queue of gamma retries
+//   small lambda    inversion with one uniform, MX_PS_TERMS terms unrolled and branch-free in the form
+//                   t_k = lambda^k e^-lambda, d_k = cdf(k) - u (3 instructions per term); the few still
+//                   open continue in a loop with a vote every 4 terms; top 2^-12 of the uniforms in fp64
+//   large lambda    PTRS, two trials per Philox block; rejected entries return to the queue
+// The Philox blocks of a count are the ones mixture_step uses (2a: gamma attempt a, 2a+1: Poisson attempt
+// a of the (cell, gene) stream), so the gamma and PTRS stages draw the very numbers the hybrid kernel's
+// mixture path would.  Work decomposition, scheduler and row grouping as in draw_counts_kernel.  Every
+// count is written exactly once, by the stage that finishes it (4-byte stores; the entries of a batch
+// are neighbouring lanes' genes of one cell, 16 bytes apart, and the other three genes of each quad
+// follow within the same iteration: the sectors are completed in L2).
+// ---------------------------------------------------------------------------
+#ifndef MX_PS_TERMS
+#define MX_PS_TERMS 12                       // unrolled terms of the small-lambda inversion (8 / 12 / 16 measured)
+#endif
+#ifndef MX_MIN_CTAS
+#define MX_MIN_CTAS 7
+#endif
+#ifndef MX_DENSE_GAMMA
+#define MX_DENSE_GAMMA 1                     // branch-free Marsaglia-Tsang attempt (gamma_attempt_dense)
+#endif
+constexpr int MX_CAP = 160;                  // 31 carried + 128 new entries per cell iteration, rounded up
+enum : int { MX_Q_GAMMA = 0, MX_Q_SMALL = 1, MX_Q_LARGE = 2 };
+struct MxWarpQueues {
+  float4 q[3][MX_CAP];         // gamma retries: mu, theta, cell, gene | small lambda: lambda, cell, gene, - |
+                               // PTRS: lambda, cell, gene, attempt
+  unsigned char g_att[MX_CAP]; // attempt number of a gamma retry (1..62)
+};
+
+template <bool VEC, bool STATS>
+__global__ void __launch_bounds__(HY_THREADS, MX_MIN_CTAS)
+draw_counts_mixture_kernel(uint32_t key0, uint32_t key1, const float *__restrict__ means, uint32_t G, uint32_t Q,
+                           const float *__restrict__ scaling, const float *__restrict__ alpha,
+                           const float *__restrict__ beta_m1, int64_t cell0, int32_t *__restrict__ X, uint32_t ldx,
+                           uint32_t *__restrict__ flags, const uint32_t *__restrict__ hdr,
+                           const int32_t *__restrict__ order, const uint4 *__restrict__ groups, int sched,
+                           unsigned long long *__restrict__ gene_sum, unsigned long long *__restrict__ gene_sumsq,
+                           unsigned long long *__restrict__ gene_zeros) {
+  __shared__ MxWarpQueues queues[HY_WARPS];
+  MxWarpQueues &wq = queues[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint32_t n_strips = (Q + 31u) / 32u;
+  const uint64_t n_chunks = (uint64_t)hdr[1] * n_strips;
+  const int64_t n_warps = (int64_t)gridDim.x * HY_WARPS;
+  constexpr float inv_fact[34] = PST_INV_FACT_TABLE;
+  static_assert(MX_PS_TERMS >= 4 && MX_PS_TERMS <= 24, "lambda^k e^-lambda, lambda < 10, must stay in fp32 range");
+  int ng = 0, ns = 0, nl = 0;                // queue fills (gamma retries, small lambda, PTRS), warp-uniform
+  uint32_t flag = 0;
+  const uint64_t keep = l2_policy_evict_last();
+
+  // a finished count: the only store this element ever gets
+  auto write_count = [&](int cell, int gene, float value) {
+    int val = (int)value;
+    if (value > 2147483520.f) { val = 2147483647; flag |= PST_FLAG_CLAMPED; }
+    X[(uint64_t)(uint32_t)cell * ldx + (uint32_t)gene] = val;
+    if constexpr (STATS) {
+      if (val > 0) {
+        atomicAdd(gene_sum + gene, (unsigned long long)val);
+        atomicAdd(gene_sumsq + gene, (unsigned long long)val * (unsigned long long)val);
+      } else {
+        atomicAdd(gene_zeros + gene, 1ull);
+      }
+    }
+  };
+  // queue appends: every lane calls, `p` says whether it has an entry
+  auto push_large = [&](bool p, float lam, int cell, int gene, int att) {
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (p) wq.q[MX_Q_LARGE][nl + __popc(m & lt_mask)] =
+        make_float4(lam, __int_as_float(cell), __int_as_float(gene), __int_as_float(att));
+    nl += __popc(m);
+  };
+  // one Marsaglia-Tsang attempt (block 2 att of the count's stream) ...
+  auto gamma_draw = [&](float mu, float th, int cell, int gene, int att, float &lam) -> bool {
+    const int64_t gcell = cell0 + cell;
+    const uint4 w = philox_s(key0, key1, (uint32_t)gene, (uint32_t)gcell,
+                             (TAG_COUNT << 16) | (uint32_t)((uint64_t)gcell >> 32), 2u * (uint32_t)att);
+#if MX_DENSE_GAMMA
+    return gamma_attempt_dense(mu, th, w, att >= 62, lam);
+#else
+    lam = 0.f;
+    return gamma_attempt(mu, th, w, att >= 62, lam);
+#endif
+  };
+  // ... and the routing of its outcome: an accepted lambda to the Poisson queue of its size, a rejected
+  // attempt to the gamma retries.  One slot computation and one 16-byte store serve the three queues.
+  auto gamma_route = [&](bool act, bool ok, float lam, float mu, float th, int cell, int gene, int att, uint32_t pword) {
+    const bool small = lam < 10.f;
+    const unsigned m_s = __ballot_sync(0xffffffffu, act && ok && small);
+    const unsigned m_l = __ballot_sync(0xffffffffu, act && ok && !small);
+    const unsigned m_g = __ballot_sync(0xffffffffu, act && !ok);
+    const int which = ok ? (small ? MX_Q_SMALL : MX_Q_LARGE) : MX_Q_GAMMA;
+    const int at = ok ? (small ? ns + __popc(m_s & lt_mask) : nl + __popc(m_l & lt_mask)) : ng + __popc(m_g & lt_mask);
+    const float cf = __int_as_float(cell), gf = __int_as_float(gene);
+    // fourth word: the inversion's uniform (small lambda) or PTRS attempt 0
+    if (act) (&wq.q[0][0])[which * MX_CAP + at] =
+        ok ? make_float4(lam, cf, gf, small ? __uint_as_float(pword) : 0.f) : make_float4(mu, th, cf, gf);
+    if (act && !ok) wq.g_att[at] = (unsigned char)(att + 1);
+    ns += __popc(m_s);
+    nl += __popc(m_l);
+    ng += __popc(m_g);
+  };
+  // The uniform of a small-lambda inversion: word (gene mod 4) of block 1 of the (cell, gene quad) stream, so
+  // that the lane that owns a quad forms the four of them with ONE Philox block; a gamma retry forms its own.
+  auto poisson_block = [&](int cell, uint32_t quad) -> uint4 {
+    const int64_t gcell = cell0 + cell;
+    return philox_s(key0, key1, quad, (uint32_t)gcell, (TAG_QUAD << 16) | (uint32_t)((uint64_t)gcell >> 32), 1u);
+  };
+  auto poisson_word = [&](int cell, int gene) -> uint32_t {
+    const uint4 b = poisson_block(cell, (uint32_t)gene >> 2);
+    const uint32_t j4 = (uint32_t)gene & 3u;
+    return j4 == 0 ? b.x : j4 == 1 ? b.y : j4 == 2 ? b.z : b.w;
+  };
+  auto drain_gamma = [&](int first, int cnt) {
+    const bool act = lane < cnt;
+    float4 g = make_float4(1.f, 1.f, 0.f, 0.f);
+    int att = 1;
+    if (act) { g = wq.q[MX_Q_GAMMA][first + lane]; att = wq.g_att[first + lane]; }
+    __syncwarp();                                   // every entry is read before its slot is reused
+    const int cell = __float_as_int(g.z), gene = __float_as_int(g.w);
+    float lam;
+    const bool ok = gamma_draw(g.x, g.y, cell, gene, att, lam);
+    gamma_route(act, ok, lam, g.x, g.y, cell, gene, att, poisson_word(cell, gene));
+    __syncwarp();
+  };
+  // Poisson(lambda), lambda < 10, by inversion with the uniform that came with the entry: no Philox here
+  auto drain_small = [&](int first, int cnt) {
+    const bool act = lane < cnt;
+    const float4 e = act ? wq.q[MX_Q_SMALL][first + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float lam = e.x;
+    const int2 cg = make_int2(__float_as_int(e.y), __float_as_int(e.z));
+    const uint32_t word = __float_as_uint(e.w);      // the uniform came with the entry (poisson_word)
+    const float u = u01(word);
+    float t = exp_fast(-lam);                          // t_k = lambda^k e^-lambda = P(k) k!
+    float d = t - u;                                 // cdf(0) - u
+    int cn = (int)(__float_as_uint(d) >> 31);        // X = #{k : u > cdf(k)}
+#pragma unroll
+    for (int k = 1; k <= MX_PS_TERMS; ++k) {
+      t *= lam;
+      d = fmaf(t, inv_fact[k], d);
+      cn += (int)(__float_as_uint(d) >> 31);
+    }
+    if (__any_sync(0xffffffffu, d < 0.f)) {          // lambda close to 10 and a large uniform: P(k) form from here
+      float pp = t * inv_fact[MX_PS_TERMS];
+      for (int k = MX_PS_TERMS; k < 96; k += 4) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+          pp *= div_fast(lam, (float)(k + s4 + 1));
+          d += pp;
+          cn += (int)(__float_as_uint(d) >> 31);
+        }
+        if (!__any_sync(0xffffffffu, d < 0.f)) break;
+      }
+    }
+    if (act && word >= 0xFFF00000u) {
+      // top 2^-12 of the uniforms: fp32 cannot resolve the cdf next to 1 (and its uniform has 24 bits), so
+      // the far tail is inverted with 32 more random bits (block 1 of the count's own stream) against a
+      // cdf accumulated in fp64
+      const int64_t gcell = cell0 + cg.x;
+      const uint4 w = philox_s(key0, key1, (uint32_t)cg.y, (uint32_t)gcell,
+                               (TAG_COUNT << 16) | (uint32_t)((uint64_t)gcell >> 32), 1u);
+      const double u64 = ((double)word + ((double)w.x + 0.5) * 2.3283064365386963e-10) * 2.3283064365386963e-10;
+      const double dl = (double)lam;
+      double p = exp(-dl), cdf = p, kk = 0.0;
+      while (u64 > cdf && kk < 1024.0) { kk += 1.0; p *= dl / kk; cdf += p; }
+      cn = (int)kk;
+    }
+    if (act) write_count(cg.x, cg.y, (float)cn);
+    __syncwarp();                                   // every entry is read before its slot is reused
+  };
+  // Poisson(lambda), lambda >= 10: two PTRS trials from Philox block 2 att + 1; rejected entries come back
+  auto drain_large = [&](int first, int cnt) {
+    const bool act = lane < cnt;
+    const float4 e = act ? wq.q[MX_Q_LARGE][first + lane] : make_float4(100.f, 0.f, 0.f, 0.f);
+    __syncwarp();                                   // every entry is read before its slot is reused
+    const float lam = e.x;
+    const int cell = __float_as_int(e.y), gene = __float_as_int(e.z), att = __float_as_int(e.w);
+    const int64_t gcell = cell0 + cell;
+    const uint4 w = philox_s(key0, key1, (uint32_t)gene, (uint32_t)gcell,
+                             (TAG_COUNT << 16) | (uint32_t)((uint64_t)gcell >> 32), 2u * (uint32_t)att + 1u);
+    float k;
+    bool ok = true;
+    if (lam < 1.6e7f) {
+      const float slam = lam * rsqrt_fast(lam), loglam = log_fast(lam);
+      const float b = fmaf(2.53f, slam, 0.931f);
+      const float a = fmaf(0.02483f, b, -0.059f);
+      const float log_inv_alpha = log_fast(1.1239f + div_fast(1.1328f, b - 3.4f));
+      const float vr = 0.9277f - div_fast(3.6224f, b - 2.0f);
+      ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.x) - 0.5f, u01(w.y), k);
+      if (!ok) ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.z) - 0.5f, u01(w.w), k);
+      ok = ok || att >= 62;                          // never reached in practice
+      k = fmaxf(k, 0.f);
+    } else {                                         // beyond 2^24: normal limit (TV error < 1e-4)
+      k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * log_fast(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));
+    }
+    if (act && ok) write_count(cell, gene, k);
+    push_large(act && !ok, lam, cell, gene, att + 1);
+    __syncwarp();
+  };
+  // run the queues down to fewer than `limit` entries each (32 while sampling, 1 at the end)
+  auto run_queues = [&](int limit) {
+    while (ns >= limit || nl >= limit || ng >= limit) {
+      while (ns >= limit) { const int c = ns < 32 ? ns : 32; ns -= c; drain_small(ns, c); }
+      while (nl >= limit) { const int c = nl < 32 ? nl : 32; nl -= c; drain_large(nl, c); }
+      if (ng >= limit) { const int c = ng < 32 ? ng : 32; ng -= c; drain_gamma(ng, c); }
+    }
+  };
+
+  for (;;) {
+    unsigned claimed = 0;
+    if (lane == 0) claimed = atomicAdd(&g_sched[sched][0], 1u);
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    if ((uint64_t)claimed >= n_chunks) break;
+    const uint32_t grp = claimed / n_strips;
+    const uint32_t strip = claimed - grp * n_strips;
+    const uint4 gd = __ldg(groups + grp);                     // first position in `order`, cells, tree row
+    const uint32_t pos0 = gd.x;
+    const int n_cells = (int)gd.y;
+    const bool lane_first = strip * 32u + (uint32_t)lane < Q;     // lanes past the last quad have no work
+    const uint32_t quad = min(strip * 32u + (uint32_t)lane, Q - 1u);
+    const uint32_t g0 = quad * 4u;
+    float m[4], c[4], bm[4];
+    bool chunk_clean;
+    {
+      float al[4];
+      const float *mrow = means + (uint64_t)gd.z * G + g0;
+      if (VEC) {
+        const float4 av = __ldg(reinterpret_cast<const float4 *>(alpha + g0));
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(beta_m1 + g0));
+        const float4 mv = ldg_f4_hint(mrow, keep);
+        al[0] = av.x; al[1] = av.y; al[2] = av.z; al[3] = av.w;
+        bm[0] = bv.x; bm[1] = bv.y; bm[2] = bv.z; bm[3] = bv.w;
+        m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = g0 + j < G;
+          al[j] = ok ? alpha[g0 + j] : 0.f;
+          bm[j] = ok ? beta_m1[g0 + j] : 1.f;
+          m[j] = ok ? mrow[j] : 1.f;
+        }
+      }
+      bool fine = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c[j] = al[j] * m[j];
+        fine = fine && (m[j] > 1e-20f) && (m[j] < 1e30f) && (c[j] >= 0.f) && (c[j] < 1e30f) && (bm[j] > 0.f) && (bm[j] < 1e30f);
+      }
+      chunk_clean = __all_sync(0xffffffffu, fine);
+    }
+    int32_t meta_cell = 0; float meta_s = 1.f;
+    auto load_meta = [&](int first) {                       // cells first .. first+31 of this group
+      const int i = first + lane;
+      meta_cell = order[pos0 + (uint32_t)(i < n_cells ? i : n_cells - 1)];
+      meta_s = scaling[meta_cell];
+      // a library size that is not positive and finite is flagged and sampled as NaN (domain error: counts 0)
+      if (!(meta_s > 0.f && meta_s < 3.0e38f)) { flag |= PST_FLAG_DOMAIN; meta_s = __int_as_float(0x7fc00000); }
+    };
+    load_meta(0);
+    for (int ci = 0; ci < n_cells; ++ci) {
+      const int src = ci & 31;
+      const int32_t cell = __shfl_sync(0xffffffffu, meta_cell, src);
+      const float s = __shfl_sync(0xffffffffu, meta_s, src);
+      if (src == 31) load_meta(ci + 1);
+      // the four attempts of the quad first (four independent chains of Philox and MUFU latencies in
+      // flight), then their routing
+      float mu[4], th[4], lam[4];
+      bool go[4], ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mu[j] = m[j] * s;
+        th[j] = fmaf(c[j], s, bm[j]);
+        go[j] = lane_first && (VEC || g0 + j < G);
+      }
+      // mean and theta are positive and finite for every gene of a clean chunk and a library size in range:
+      // only the other (cell, strip) pairs check count by count
+      if (!(chunk_clean && s > 1e-15f && s < 1e8f)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!nb_domain_ok(mu[j], th[j])) {               // scipy's "Domain error": flagged, the count is 0
+            if (go[j]) {
+              flag |= PST_FLAG_DOMAIN;
+              X[(uint64_t)(uint32_t)cell * ldx + g0 + j] = 0;
+              if constexpr (STATS) atomicAdd(gene_zeros + g0 + j, 1ull);
+            }
+            go[j] = false;
+            mu[j] = 1.f;
+            th[j] = 1.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ok[j] = gamma_draw(mu[j], th[j], (int)cell, (int)(g0 + j), 0, lam[j]);
+      const uint4 pb = poisson_block((int)cell, quad);
+      const uint32_t pw[4] = {pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gamma_route(go[j], ok[j], lam[j], mu[j], th[j], (int)cell, (int)(g0 + j), 0, pw[j]);
+      __syncwarp();
+      run_queues(32);
+    }
+  }
+  __syncwarp();
+  run_queues(1);
+  if (flag) atomicOr(flags, flag);
+  if (lane == 0) {                                            // the last warp to leave rearms the scheduler words
     const unsigned done = atomicAdd(&g_sched[sched][1], 1u);
     if (done == (unsigned)n_warps - 1u) { g_sched[sched][0] = 0u; g_sched[sched][1] = 0u; __threadfence(); }
   }
@@ -1119,24 +1456,30 @@ extern "C" int pst_draw_counts(const float *means, int64_t P, int64_t G, const i
   const unsigned hb = (unsigned)(need < cap ? need : cap);
   const uint32_t tail_cap = (uint32_t)L.tail_cap;
   typedef unsigned long long ull;
-#define PST_LAUNCH_DRAW2(V, MIX, ST)                                                                                \
-    draw_counts_kernel<HY_KFIX, V, MIX, ST><<<hb, HY_THREADS, 0, st>>>(                                             \
+#define PST_LAUNCH_DRAW(V, ST)                                                                                      \
+    draw_counts_kernel<HY_KFIX, V, ST><<<hb, HY_THREADS, 0, st>>>(                                                  \
         PhiloxKey(seed), means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags,  \
         scratch, order, groups, slot, scratch, tail_cap, (ull *)gene_sum, (ull *)gene_sumsq, (ull *)gene_zeros)
-#define PST_LAUNCH_DRAW(MIX)                                                                                        \
-  do {                                                                                                              \
-    if (vec && stats) PST_LAUNCH_DRAW2(true, MIX, true);                                                            \
-    else if (vec) PST_LAUNCH_DRAW2(true, MIX, false);                                                               \
-    else if (stats) PST_LAUNCH_DRAW2(false, MIX, true);                                                             \
-    else PST_LAUNCH_DRAW2(false, MIX, false);                                                                       \
-  } while (0)
-  if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture queue
-    PST_LAUNCH_DRAW(true);
+  if (sampler == PST_SAMPLER_GAMMA_POISSON) {            // every count through the mixture pipeline
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int64_t mcap = (int64_t)num_sm() * MX_MIN_CTAS;
+    const unsigned mb = (unsigned)(need < mcap ? need : mcap);
+#define PST_LAUNCH_MIX(V, ST)                                                                                       \
+    draw_counts_mixture_kernel<V, ST><<<mb, HY_THREADS, 0, st>>>(                                                   \
+        k0, k1, means, (uint32_t)G, (uint32_t)Q, scaling, alpha, beta_m1, cell0, X, (uint32_t)ldx, flags, scratch,  \
+        order, groups, slot, (ull *)gene_sum, (ull *)gene_sumsq, (ull *)gene_zeros)
+    if (vec && stats) PST_LAUNCH_MIX(true, true);
+    else if (vec) PST_LAUNCH_MIX(true, false);
+    else if (stats) PST_LAUNCH_MIX(false, true);
+    else PST_LAUNCH_MIX(false, false);
+#undef PST_LAUNCH_MIX
     return check_launch(fn);
   }
-  PST_LAUNCH_DRAW(false);
+  if (vec && stats) PST_LAUNCH_DRAW(true, true);
+  else if (vec) PST_LAUNCH_DRAW(true, false);
+  else if (stats) PST_LAUNCH_DRAW(false, true);
+  else PST_LAUNCH_DRAW(false, false);
 #undef PST_LAUNCH_DRAW
-#undef PST_LAUNCH_DRAW2
   rc = check_launch(fn);
   if (rc) return rc;
   // the listed counts (2^-14 of the inverted ones): one thread each, grid-stride beyond the expectation

@@ -11,6 +11,9 @@
 #include <sys/mman.h>
 #include <unistd.h>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "../../include/prosstt_b200.h"
@@ -25,19 +28,66 @@ int clamp_threads(int threads, int64_t n, int64_t min_per_thread) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 256), useful));
 }
 
+// Worker threads that outlive the calls: an expansion runs once per staged chunk (every few
+// milliseconds), and starting 15 threads each time costs a visible share of it.  One job at a time
+// (callers queue on run_m_); the caller works too.  Never destroyed (threads die with the process); a
+// forked child starts its own.
+class Pool {
+ public:
+  static Pool &get() {
+    static Pool *pool = nullptr;
+    static std::mutex guard;
+    std::lock_guard<std::mutex> g(guard);
+    if (pool == nullptr || pool->pid_ != getpid()) pool = new Pool();
+    return *pool;
+  }
+  void run(int tasks, const std::function<void(int)> &fn) {
+    if (tasks <= 1) { if (tasks == 1) fn(0); return; }
+    std::lock_guard<std::mutex> one_job(run_m_);
+    std::unique_lock<std::mutex> lk(m_);
+    while ((int)th_.size() < tasks - 1) th_.emplace_back([this] { work(); });
+    fn_ = &fn; tasks_ = tasks; next_ = 0; done_ = 0;
+    cv_.notify_all();
+    take(lk);
+    done_cv_.wait(lk, [this] { return done_ == tasks_; });
+    fn_ = nullptr; tasks_ = 0; next_ = 0;
+  }
+
+ private:
+  Pool() : pid_(getpid()) {}
+  void take(std::unique_lock<std::mutex> &lk) {              // called with m_ held
+    while (next_ < tasks_) {
+      const int t = next_++;
+      lk.unlock();
+      (*fn_)(t);
+      lk.lock();
+      if (++done_ == tasks_) done_cv_.notify_all();
+    }
+  }
+  void work() {
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      cv_.wait(lk, [this] { return next_ < tasks_; });
+      take(lk);
+    }
+  }
+  std::mutex run_m_, m_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> th_;
+  const std::function<void(int)> *fn_ = nullptr;
+  int tasks_ = 0, next_ = 0, done_ = 0;
+  pid_t pid_;
+};
+
 // run fn(lo, hi) over [0, n) cut into `threads` contiguous slices aligned to 64 elements
 template <class F>
 void parallel_slices(int64_t n, int threads, F fn) {
   if (threads <= 1) { fn((int64_t)0, n); return; }
-  std::vector<std::thread> pool;
-  pool.reserve(threads - 1);
   const int64_t per = ((n + threads - 1) / threads + 63) & ~(int64_t)63;
-  for (int t = 1; t < threads; ++t) {
+  Pool::get().run(threads, [&](int t) {
     const int64_t lo = std::min(n, per * t), hi = std::min(n, per * (t + 1));
-    if (lo < hi) pool.emplace_back([=] { fn(lo, hi); });
-  }
-  fn((int64_t)0, std::min(n, per));
-  for (auto &th : pool) th.join();
+    if (lo < hi) fn(lo, hi);
+  });
 }
 
 template <class S, class D>
@@ -168,12 +218,17 @@ extern "C" int pst_host_apply_overflow(void *dst, int32_t dst_bits, int64_t base
                                        const int32_t *value, int64_t entries) {
   if (entries < 0 || n < 0 || (entries > 0 && (!dst || !index || !value))) return -1;
   if (dst_bits != 32 && dst_bits != 64) return -1;
-  for (int64_t i = 0; i < entries; ++i) {
-    const int64_t at = index[i] - base;
-    if (at < 0 || at >= n) continue;
-    if (dst_bits == 32) static_cast<int32_t *>(dst)[at] = value[i];
-    else static_cast<int64_t *>(dst)[at] = (int64_t)value[i];
-  }
+  // scattered single-element writes (each one a cache miss in a matrix of gigabytes): a few threads keep
+  // more of them in flight; an index listed twice carries the same value, so slices need no ordering
+  const int threads = std::min(clamp_threads(0, entries, 1 << 14), 16);
+  parallel_slices(entries, threads, [=](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      const int64_t at = index[i] - base;
+      if (at < 0 || at >= n) continue;
+      if (dst_bits == 32) static_cast<int32_t *>(dst)[at] = value[i];
+      else static_cast<int64_t *>(dst)[at] = (int64_t)value[i];
+    }
+  });
   return 0;
 }
 

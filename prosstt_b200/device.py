@@ -218,6 +218,7 @@ _STAGING = {}
 
 
 _WIDEN_RATE = {}
+_AUTO_STATE = {"narrow_overflowed": False}     # an automatically chosen uint8 transport overflowed its list once
 
 
 def _widen_rate(threads):
@@ -343,8 +344,10 @@ class CountEngine(object):
           PCIe in the transport format into pinned staging buffers (cached per device) and host threads
           (pst_host_widen) expand it into host_out, the overflow list is applied at the end: the caller
           receives exact int32 / int64 counts.  This is the path of the reference-shaped call, which
-          returns a fresh (pageable) int64 array.  Default transport: "i32" for pageable targets; for a
-          pinned int32 target the faster of "direct" and "u8" on this host (_shared_host_transport).
+          returns a fresh (pageable) int64 array.  Default transport: the wide one ("direct" for a pinned
+          int32 tensor, "i32" otherwise) or "u8", whichever is faster on this host (_shared_host_transport);
+          an automatically chosen "u8" whose overflow list does not fit (deep regimes) is sampled again
+          through the wide transport - the counts are the same either way.
           The expansion uses streaming stores (pst_host_widen_stream) unless `fresh` says that host_out was
           just allocated and never touched (its pages are zeroed into the cache by the first-touch faults)."""
         n = int(rows.numel())
@@ -363,15 +366,35 @@ class CountEngine(object):
         narrow_dst = hdt in (torch.uint16, torch.uint8)
         if not threads:
             threads = _host_threads()
-        if transport is None and not is_np and hdt == torch.int32 and pinned:
-            transport = _shared_host_transport(threads)
+        auto = transport is None
+        wide = None
+        if auto and not narrow_dst:
+            # nothing asked for: the copy engine writes a pinned int32 matrix itself ("direct"), every other
+            # target is filled by host threads from int32 staging ("i32") - or, where this rank's share of
+            # the host cores expands uint8 well above the PCIe rate, from uint8 staging ("u8")
+            wide = "direct" if (not is_np and hdt == torch.int32 and pinned) else "i32"
+            transport = wide
+            if not _AUTO_STATE["narrow_overflowed"] and _shared_host_transport(threads) == "u8":
+                transport = "u8"
         if transport in (None, "direct") and not is_np and hdt != torch.int64 and \
                 (pinned or narrow_dst or transport == "direct"):
             return self._draw_to_host_direct(rows, scaling32, seed, cell0, host_out, chunk_cells, overflow_cap)
         if narrow_dst:
             raise ValueError("a uint16 / uint8 host matrix must be a CPU tensor and takes transport 'direct'")
-        return self._draw_to_host_staged(rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
-                                         transport or "i32", threads, fresh)
+        try:
+            return self._draw_to_host_staged(rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, overflow_cap,
+                                             transport or "i32", threads, fresh)
+        except OverflowError:
+            if not (auto and transport == "u8"):
+                raise
+        # A deep regime (more than 1 % of the counts above 254): the uint8 transport nobody asked for does not
+        # pay here.  The draw is a pure function of (seed, cell, gene): sample again through the wide transport,
+        # and keep to it for the rest of the process.
+        _AUTO_STATE["narrow_overflowed"] = True
+        if wide == "direct":
+            return self._draw_to_host_direct(rows, scaling32, seed, cell0, host_out, chunk_cells, None)
+        return self._draw_to_host_staged(rows, scaling32, seed, cell0, host_out, hdt, chunk_cells, None,
+                                         "i32", threads, False)
 
     def stream_chunks(self, rows, scaling32, seed, cell0, consume, transport="i32", chunk_cells=None,
                       overflow_cap=None):
@@ -388,6 +411,7 @@ class CountEngine(object):
             raise ValueError("transport must be 'i32', 'u16' or 'u8'")
         width = torch.empty(0, dtype=tdt).element_size()
         narrow = width < 4
+        ramp_up = chunk_cells is None
         if chunk_cells is None:
             chunk_cells = max(1, min(n, _STAGE_BYTES // max(1, width * G)))
         if narrow and overflow_cap is None:
@@ -409,9 +433,16 @@ class CountEngine(object):
             event.synchronize()                     # the chunk is in stage_host[k]
             consume(stage_host[k][:(hi - lo) * G * width], lo, hi)
 
+        # the first chunks are smaller so that the copy and the consumer start almost immediately
+        bounds, lo = [], 0
+        ramp = [max(1, chunk_cells // 8), max(1, chunk_cells // 4), max(1, chunk_cells // 2)] if ramp_up else []
+        while lo < n:
+            size = ramp.pop(0) if ramp else chunk_cells
+            bounds.append((lo, min(n, lo + size)))
+            lo = bounds[-1][1]
         try:
-            for i, lo in enumerate(range(0, n, chunk_cells)):
-                hi, k = min(n, lo + chunk_cells), i & 1
+            for i, (lo, hi) in enumerate(bounds):
+                k = i & 1
                 if pending[k] is not None:
                     pending[k].result()             # stage_host[k] (and so stage_dev[k]) is free again
                 buf = stage_dev[k][:hi - lo]

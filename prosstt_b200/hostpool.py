@@ -1,0 +1,92 @@
+"""Recycled host memory for the result matrices of the reference-shaped calls.
+
+`sample_density(tree, N, alpha, beta)` returns a fresh int64 NumPy matrix like the reference does
+(simulation.py:651): 8 B per count of host memory that nobody has touched yet, so the threads that
+expand the counts into it take one page fault (and one page of zeroing) per 4 KiB - measured 5.5e9
+counts/s with 16 threads, against 1.3-1.8e10 into memory that is already mapped
+(profiles/r02_host_bw_1gpu.txt).  A script that samples more than once (every notebook of the
+reference does) drops the previous result before or while it asks for the next one, so the buffer of
+a result that has been garbage-collected is kept here and handed out again: same array semantics
+(writeable, C-contiguous, views keep it alive), no page faults from the second call on.
+
+Only matrices of at least 4 MiB are pooled; at most PST_HOST_POOL_GB (default: a quarter of the
+physical memory) of free buffers is retained; `release()` returns them to the OS; PST_HOST_POOL_GB=0
+disables the pool (every result is then `np.empty`)."""
+import mmap
+import os
+import threading
+import weakref
+
+import numpy as np
+
+_LOCK = threading.Lock()
+_FREE = []                    # [nbytes, mmap] of results that were garbage-collected, pages mapped
+_MIN_BYTES = 4 << 20
+_HUGE = 2 << 20
+
+
+def _cap_bytes():
+    env = os.environ.get("PST_HOST_POOL_GB")
+    if env is not None:
+        try:
+            return max(0, int(float(env) * (1 << 30)))
+        except ValueError:
+            return 0
+    try:
+        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 4
+    except (ValueError, OSError, AttributeError):
+        return 0
+
+
+def _give_back(buf, size):
+    cap = _cap_bytes()
+    with _LOCK:
+        _FREE.append([size, buf])
+        total = sum(b[0] for b in _FREE)
+        while _FREE and total > cap:                 # oldest first
+            total -= _FREE.pop(0)[0]
+
+
+def release():
+    """Return every retained buffer to the OS."""
+    with _LOCK:
+        del _FREE[:]
+
+
+def retained_bytes():
+    with _LOCK:
+        return sum(b[0] for b in _FREE)
+
+
+def result_array(shape, dtype):
+    """(array, fresh): a writeable C-contiguous array of `shape`/`dtype` and whether its memory has never
+    been touched (then the first writes fault its pages in)."""
+    dtype = np.dtype(dtype)
+    count = 1
+    for d in shape:
+        count *= int(d)
+    nbytes = count * dtype.itemsize
+    if nbytes < _MIN_BYTES or _cap_bytes() == 0:
+        return np.empty(shape, dtype=dtype), True
+    need = (nbytes + _HUGE - 1) // _HUGE * _HUGE
+    buf = None
+    with _LOCK:
+        best = None
+        for i, (size, _) in enumerate(_FREE):        # smallest retained buffer that fits without wasting half
+            if need <= size <= 2 * need and (best is None or size < _FREE[best][0]):
+                best = i
+        if best is not None:
+            need, buf = _FREE.pop(best)
+    fresh = buf is None
+    if fresh:
+        buf = mmap.mmap(-1, need)
+        if hasattr(buf, "madvise") and hasattr(mmap, "MADV_HUGEPAGE"):
+            try:
+                buf.madvise(mmap.MADV_HUGEPAGE)
+            except OSError:
+                pass
+    # `owner` is the object every view of the result keeps alive (NumPy does not collapse a base chain
+    # past a non-ndarray buffer); when the last of them is gone the mapping comes back to the pool
+    owner = np.frombuffer(buf, dtype=np.uint8)
+    weakref.finalize(owner, _give_back, buf, need).atexit = False
+    return owner[:nbytes].view(dtype).reshape(shape), fresh

@@ -33,6 +33,7 @@ import torch
 
 from prosstt_b200 import _native as nat
 from prosstt_b200 import count_model as cm
+from prosstt_b200 import hostpool
 from prosstt_b200 import sim_utils as sut
 from prosstt_b200.device import CountEngine, TreeTables, choice_cdf, raise_flags, tree_tables
 from prosstt_b200.sharding import shard_range
@@ -421,10 +422,11 @@ def _sample_counts(engine, rows, s32, seed, first, dtype, out):
     want = np.dtype(dtype)
     n = int(rows.numel())
     direct = want in (np.dtype(np.int32), np.dtype(np.int64))
-    host = np.empty((n, engine.G), dtype=want if direct else np.int64)
-    nat.load().pst_host_prepare(host.ctypes.data, host.nbytes)       # huge pages under the fresh result
+    # a fresh matrix - or the memory of an earlier result that has been garbage-collected (hostpool: no page
+    # faults from the second call on)
+    host, fresh = hostpool.result_array((n, engine.G), want if direct else np.int64)
     if n and engine.G:
-        engine.draw_to_host(rows, s32, seed, first, host, fresh=True)     # untouched pages: ordinary stores
+        engine.draw_to_host(rows, s32, seed, first, host, fresh=fresh)    # untouched pages: ordinary stores
     torch.cuda.current_stream(engine.dev).synchronize()
     engine.check()
     return host if direct else host.astype(want)

@@ -331,3 +331,45 @@ def test_host_side_helpers_of_the_device_to_host_path():
     assert lib.pst_draw_scratch_layout(1000, 400, 37, lay) == 0
     assert lib.pst_draw_scratch_words(1000, 400, 37) == lay[4] + 4 * lay[5] and lay[4] % 4 == 0
     assert lay[1] == 4 + 4 * lay[0] and lay[2] == lay[1] + 1000 and lay[3] == lay[2] + 38
+
+
+def test_result_pool_recycles_only_unreachable_matrices():
+    """hostpool: the buffer of a result comes back when the array AND every view of it are gone, is handed
+    out again for a matrix of similar size, and PST_HOST_POOL_GB=0 turns the pool off."""
+    import gc
+    from prosstt_b200 import hostpool as hp
+    hp.release()
+    a, fresh = hp.result_array((1000, 2000), np.int64)
+    assert fresh and a.shape == (1000, 2000) and a.dtype == np.int64
+    assert a.flags.writeable and a.flags.c_contiguous
+    a[:] = 7
+    view = a[10:20, ::2]
+    del a
+    gc.collect()
+    assert hp.retained_bytes() == 0 and (view == 7).all()          # a view keeps the memory out of the pool
+    del view
+    gc.collect()
+    assert hp.retained_bytes() == 16 << 20
+    b, fresh = hp.result_array((999, 2000), np.int64)              # similar size: the same memory again
+    assert not fresh and hp.retained_bytes() == 0 and b.shape == (999, 2000)
+    c, fresh = hp.result_array((999, 2000), np.int64)              # the first is still alive: new memory
+    assert fresh
+    del b, c
+    gc.collect()
+    small, fresh = hp.result_array((100, 2000), np.int32)          # far smaller than what is retained: not reused
+    assert fresh and small.flags.owndata
+    hp.release()
+    assert hp.retained_bytes() == 0
+    old = os.environ.get("PST_HOST_POOL_GB")
+    os.environ["PST_HOST_POOL_GB"] = "0"
+    try:
+        d, fresh = hp.result_array((1000, 2000), np.int64)
+        assert fresh and d.flags.owndata
+        del d
+        gc.collect()
+        assert hp.retained_bytes() == 0
+    finally:
+        if old is None:
+            del os.environ["PST_HOST_POOL_GB"]
+        else:
+            os.environ["PST_HOST_POOL_GB"] = old
