@@ -213,7 +213,7 @@ def raise_flags(word):
 
 _NP_TO_TORCH = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
                 np.dtype(np.uint16): torch.uint16, np.dtype(np.uint8): torch.uint8}
-_STAGE_BYTES = 256 << 20                      # one pinned staging buffer (two per device)
+_STAGE_BYTES = int(os.environ.get("PST_STAGE_MB", "256")) << 20   # one pinned staging buffer (two per device)
 _STAGING = {}
 
 

@@ -904,6 +904,59 @@ def test_fused_gene_stats_equal_the_second_pass(sampler):
             assert torch.equal(fused[k], want[k] + want2[k]), (G, n, depth, k, "second call")
 
 
+@pytest.mark.parametrize("depth", [-2.0, 0.0, 3.0])
+def test_gamma_poisson_pipeline_writes_every_count_once(depth):
+    """draw_counts_mixture_kernel (sampler "gamma_poisson"): a count is stored exactly once, by the pipeline
+    stage that finishes it (small-lambda inversion, PTRS, or the domain check), never by the head.  With the
+    matrix pre-filled with a sentinel: no sentinel survives inside [0, G), the padding beyond G is untouched,
+    the draw is deterministic, a partition of the cells gives the same bits, and the totals follow the means -
+    shallow (every lambda below 10), bench depth, and deep (PTRS queue and gamma retries busy); G a multiple of
+    4 (vector parameter loads) and not."""
+    dev = torch.device(DEV)
+    rng = np.random.RandomState(31)
+    for G in (1000, 1003, 130):
+        P, n, ldx = 29, 333, G + 5
+        t = ptree.Tree(topology=[], time={0: P}, num_branches=1, branch_points=0, modules=1, G=G)
+        M = np.exp(rng.normal(0.5, 1.5, size=(P, G)))
+        t.add_genes({0: M})
+        alpha = np.exp(rng.normal(np.log(0.2), 0.4, size=G))
+        beta = 1 + np.exp(rng.normal(0.0, 0.4, size=G))
+        tb = TreeTables(t, dev)
+        eng = CountEngine(t, tb, alpha, beta, dev, sampler="gamma_poisson")
+        rows_h = rng.randint(0, P, size=n)
+        sc_h = np.exp(rng.normal(depth, 0.7, size=n))
+        rows, sc = _dev(rows_h, torch.int32), _dev(sc_h, torch.float32)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        words = int(nat.load().pst_draw_scratch_words(n, G, tb.P))
+        scratch = torch.empty(words, dtype=torch.int32, device=dev)
+
+        def raw(lo, hi, out):
+            nat.call("pst_draw_counts", eng.means, tb.P, G, rows[lo:hi], sc[lo:hi], eng.alpha, eng.beta_m1, 77, 1000 + lo,
+                     hi - lo, out, ldx, status, nat.SAMPLER_GAMMA_POISSON, scratch, words, None, None, None,
+                     nat.stream_ptr(dev))
+
+        X = torch.full((n, ldx), -7, dtype=torch.int32, device=dev)
+        raw(0, n, X)
+        assert torch.all(X[:, G:] == -7) and torch.all(X[:, :G] >= 0), (G, depth)
+        again = torch.full((n, ldx), -7, dtype=torch.int32, device=dev)
+        raw(0, n, again)
+        assert torch.equal(X, again)
+        parts = torch.full((n, ldx), -7, dtype=torch.int32, device=dev)
+        raw(0, 100, parts[:100])
+        raw(100, n, parts[100:])
+        assert torch.equal(X, parts), (G, depth)
+        assert status.tolist() == [0, 0, 0, 0]
+        # totals against the means: E sum = sum mu, Var sum = sum (alpha mu^2 + beta mu)
+        mu = M[rows_h] * sc_h[:, None]
+        var = (alpha * mu ** 2 + beta * mu).sum()
+        z = (float(X[:, :G].sum(dtype=torch.int64)) - mu.sum()) / np.sqrt(var)
+        assert abs(z) < 4.5, (G, depth, z)
+        zeros = float((X[:, :G] == 0).double().mean())
+        theta = alpha * mu + beta - 1
+        p0 = np.exp(-(mu / theta) * np.log1p(theta)).mean()
+        assert abs(zeros - p0) < 5 * np.sqrt(p0 * (1 - p0) / mu.size) + 1e-4, (G, depth, zeros, p0)
+
+
 def test_count_stats_kernel_matches_numpy():
     from prosstt_b200.stats import count_stats, gene_mean_var
     rng = np.random.RandomState(6)

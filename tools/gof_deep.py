@@ -18,6 +18,8 @@ from prosstt_b200.device import CountEngine, TreeTables  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--draws", type=float, default=1e9)
 ap.add_argument("--chunk", type=int, default=50_000_000)
+ap.add_argument("--seed", type=int, default=991)
+ap.add_argument("--samplers", default="hybrid,gamma_poisson")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 regimes = [(0.3, 0.3, 2.0), (1.8, 0.2, 2.0), (6.0, 0.25, 1.6), (14.0, 0.1, 2.5), (31.9, 0.05, 1.5),
@@ -32,14 +34,14 @@ t.add_genes({"A": mu[None, :].copy(), "B": mu[None, :].copy()})
 theta = alpha * mu + beta - 1
 r, p = mu / theta, 1 / (1 + theta)
 N = int(a.draws)
-for sampler in ("hybrid", "gamma_poisson"):
+for sampler in a.samplers.split(","):
     eng = CountEngine(t, TreeTables(t, dev), alpha, beta, dev, sampler=sampler)
     hists = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(G)]
     done = 0
     while done < N:
         n = min(a.chunk, N - done)
         X = eng.draw(torch.zeros(n, dtype=torch.int32, device=dev), torch.ones(n, dtype=torch.float32, device=dev),
-                     991, done)
+                     a.seed, done)
         for g in range(G):
             h = torch.bincount(X[:, g])
             if h.numel() > hists[g].numel():
