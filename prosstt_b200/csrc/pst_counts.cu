@@ -804,6 +804,9 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
 #ifndef MX_MIN_CTAS
 #define MX_MIN_CTAS 7
 #endif
+#ifndef MX_PTRS_ONE_TRIAL
+#define MX_PTRS_ONE_TRIAL 1                  // one PTRS trial per visit of the queue (0: two, the second one divergent)
+#endif
 #ifndef MX_DENSE_GAMMA
 #define MX_DENSE_GAMMA 1                     // branch-free Marsaglia-Tsang attempt (gamma_attempt_dense)
 #endif
@@ -858,7 +861,7 @@ draw_counts_mixture_kernel(uint32_t key0, uint32_t key1, const float *__restrict
         make_float4(lam, __int_as_float(cell), __int_as_float(gene), __int_as_float(att));
     nl += __popc(m);
   };
-  // one Marsaglia-Tsang attempt (block 2 att of the count's stream) ...
+  // one Marsaglia-Tsang attempt (Philox block 2 att of the count's own stream) ...
   auto gamma_draw = [&](float mu, float th, int cell, int gene, int att, float &lam) -> bool {
     const int64_t gcell = cell0 + cell;
     const uint4 w = philox_s(key0, key1, (uint32_t)gene, (uint32_t)gcell,
@@ -928,6 +931,8 @@ draw_counts_mixture_kernel(uint32_t key0, uint32_t key1, const float *__restrict
       d = fmaf(t, inv_fact[k], d);
       cn += (int)(__float_as_uint(d) >> 31);
     }
+    const bool far = word >= 0xFFF00000u;            // decided in fp64 below: not waited for here
+    if (far) d = 1.f;
     if (__any_sync(0xffffffffu, d < 0.f)) {          // lambda close to 10 and a large uniform: P(k) form from here
       float pp = t * inv_fact[MX_PS_TERMS];
       for (int k = MX_PS_TERMS; k < 96; k += 4) {
@@ -940,7 +945,7 @@ draw_counts_mixture_kernel(uint32_t key0, uint32_t key1, const float *__restrict
         if (!__any_sync(0xffffffffu, d < 0.f)) break;
       }
     }
-    if (act && word >= 0xFFF00000u) {
+    if (act && far) {
       // top 2^-12 of the uniforms: fp32 cannot resolve the cdf next to 1 (and its uniform has 24 bits), so
       // the far tail is inverted with 32 more random bits (block 1 of the count's own stream) against a
       // cdf accumulated in fp64
@@ -964,8 +969,20 @@ draw_counts_mixture_kernel(uint32_t key0, uint32_t key1, const float *__restrict
     const float lam = e.x;
     const int cell = __float_as_int(e.y), gene = __float_as_int(e.z), att = __float_as_int(e.w);
     const int64_t gcell = cell0 + cell;
+#if MX_PTRS_ONE_TRIAL
+    // trial number att: Philox block 2 (att / 2) + 1, words (x, y) for an even and (z, w) for an odd trial -
+    // the same trials in the same order as two per visit, but a rejected entry goes back to the queue at
+    // once, so the second trial's code never runs for the few lanes that need it
+    const uint4 w4 = philox_s(key0, key1, (uint32_t)gene, (uint32_t)gcell,
+                              (TAG_COUNT << 16) | (uint32_t)((uint64_t)gcell >> 32), ((uint32_t)att | 1u));
+    const bool odd = (att & 1) != 0;
+    const uint4 w = make_uint4(odd ? w4.z : w4.x, odd ? w4.w : w4.y, 0u, 0u);
+    constexpr int kForce = 125;
+#else
     const uint4 w = philox_s(key0, key1, (uint32_t)gene, (uint32_t)gcell,
                              (TAG_COUNT << 16) | (uint32_t)((uint64_t)gcell >> 32), 2u * (uint32_t)att + 1u);
+    constexpr int kForce = 62;
+#endif
     float k;
     bool ok = true;
     if (lam < 1.6e7f) {
@@ -975,8 +992,10 @@ draw_counts_mixture_kernel(uint32_t key0, uint32_t key1, const float *__restrict
       const float log_inv_alpha = log_fast(1.1239f + div_fast(1.1328f, b - 3.4f));
       const float vr = 0.9277f - div_fast(3.6224f, b - 2.0f);
       ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.x) - 0.5f, u01(w.y), k);
+#if !MX_PTRS_ONE_TRIAL
       if (!ok) ok = ptrs_trial(lam, loglam, a, b, log_inv_alpha, vr, u01(w.z) - 0.5f, u01(w.w), k);
-      ok = ok || att >= 62;                          // never reached in practice
+#endif
+      ok = ok || att >= kForce;                      // never reached in practice
       k = fmaxf(k, 0.f);
     } else {                                         // beyond 2^24: normal limit (TV error < 1e-4)
       k = rintf(lam + sqrtf(lam) * sqrtf(-2.0f * log_fast(u01(w.x))) * __cosf(6.2831853072f * u01(w.y) - 3.1415926536f));

@@ -43,8 +43,11 @@ for name in a.samplers.split(","):
     mu_tot = (s.engine.means.double()[s.rows.long()].sum(dim=1) * s.s64).sum().item()
     tot = X.sum(dtype=torch.int64).item()
     zero = (X == 0).float().mean().item()
-    print("%-14s draw %.2f ms  -> %.3e counts/s  (%.1f GB/s)  total/expected %.5f  zeros %.4f  max %d"
+    # a position-weighted checksum: equal for two libraries only if they draw the same matrix
+    weights = (torch.arange(a.genes, device=dev, dtype=torch.int64) % 1009) + 1
+    check = int((X.to(torch.int64) * weights).sum().item()) % (1 << 61)
+    print("%-14s draw %.2f ms  -> %.3e counts/s  (%.1f GB/s)  total/expected %.5f  zeros %.4f  max %d  checksum %x"
           % (name, min(ms), a.cells * a.genes / (min(ms) / 1e3), 4 * a.cells * a.genes / (min(ms) / 1e3) / 1e9,
-             tot / mu_tot, zero, int(X.max().item())), flush=True)
+             tot / mu_tot, zero, int(X.max().item()), check), flush=True)
     del s, X
     torch.cuda.empty_cache()
