@@ -588,7 +588,7 @@ def run_e2e(a, tree, alpha, beta, sampler, dev, rank, world, barrier, max_over_r
     d2h8 = n8 + meta + listed8 * 12
     # int32 host matrix: copied as int32 by the copy engine ("direct"), or crossing PCIe as uint8 + overflow
     # list and widened by host threads ("u8").  `value` is the call with NO transport argument (the library
-    # picks one of the two from a 64 MB trial of this host's expansion rate); both are reported.
+    # picks one of the two from the CPU's store instructions and this rank's thread count); both are reported.
     by_transport = {}
     for tr in ("direct", "u8"):
         by_transport[tr] = run_pinned(torch.int32, tr)[0]

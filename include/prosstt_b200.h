@@ -283,6 +283,9 @@ int pst_host_widen(const void *h_src, int32_t src_bits, void *h_dst, int32_t dst
  * served by pst_host_widen: its pages are zeroed into the cache by the first-touch fault. */
 int pst_host_widen_stream(const void *h_src, int32_t src_bits, void *h_dst, int32_t dst_bits, int64_t n,
                           int32_t threads);
+/* 1 when pst_host_widen_stream uses non-temporal stores on this CPU, 0 when it falls back to ordinary
+ * stores (no AVX-512): the default device->host transport is chosen from this and the thread count. */
+int pst_host_stream_stores(void);
 /* Advise transparent huge pages for a freshly allocated, still untouched result buffer (the fresh
  * int64 array the reference-shaped call returns): first-touch page faults are what bounds the host
  * expansion into pageable memory.  0 = advice given, 1 = not available; never an error. */

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "pst_store_fill": (C.c_int, [_p, _i64, _i32, _p]),
     "pst_host_widen": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32]),
     "pst_host_widen_stream": (C.c_int, [_p, _i32, _p, _i32, _i64, _i32]),
+    "pst_host_stream_stores": (C.c_int, []),
     "pst_host_prepare": (C.c_int, [_p, _i64]),
     "pst_host_apply_overflow": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _i64]),
     "pst_host_checksum": (_u64, [_p, _i64, _i32]),

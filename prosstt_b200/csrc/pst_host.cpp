@@ -190,6 +190,10 @@ extern "C" int pst_host_widen(const void *src, int32_t src_bits, void *dst, int3
   return widen_any(src, src_bits, dst, dst_bits, n, threads, false);
 }
 
+// 1 when pst_host_widen_stream really uses non-temporal stores on this CPU (AVX-512), 0 when it falls
+// back to ordinary ones: what the choice of the device->host transport rests on.
+extern "C" int pst_host_stream_stores(void) { return cpu_streams() ? 1 : 0; }
+
 extern "C" int pst_host_widen_stream(const void *src, int32_t src_bits, void *dst, int32_t dst_bits, int64_t n,
                                      int32_t threads) {
   return widen_any(src, src_bits, dst, dst_bits, n, threads, true);

@@ -217,46 +217,25 @@ _STAGE_BYTES = int(os.environ.get("PST_STAGE_MB", "256")) << 20   # one pinned s
 _STAGING = {}
 
 
-_WIDEN_RATE = {}
 _AUTO_STATE = {"narrow_overflowed": False}     # an automatically chosen uint8 transport overflowed its list once
 
 
-def _widen_rate(threads):
-    """uint8 -> int32 expansion rate of this host (counts/s) with `threads` threads and streaming stores,
-    from one 64 MB trial per process and thread count (about 10 ms)."""
-    rate = _WIDEN_RATE.get(threads)
-    if rate is None:
-        import time
-        n = 1 << 24
-        src = np.zeros(n, dtype=np.uint8)
-        dst = np.empty(n, dtype=np.int32)
-        lib = nat.load()
-        best = None
-        for _ in range(3):                              # the first pass also faults the pages in
-            t0 = time.perf_counter()
-            lib.pst_host_widen_stream(src.ctypes.data, 8, dst.ctypes.data, 32, n, int(threads))
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-        rate = _WIDEN_RATE[threads] = n / max(best, 1e-9)
-    return rate
-
-
-_PCIE_INT32_RATE = 1.4e10     # counts/s of a direct int32 copy into pinned memory (55-57 GB/s, one B200 on PCIe Gen5 x16)
-
-
 def _shared_host_transport(threads):
-    """Transport of an int32 pinned host matrix when nothing was asked for.  "direct": the copy engine
-    writes the matrix, 4 B per count over PCIe (55-57 GB/s = 1.4e10 counts/s for one B200).  "u8": the
-    counts cross as uint8 + exact overflow list (a quarter of the bytes) and host threads expand them with
-    streaming stores (pst_host_widen_stream) - faster whenever this rank's share of the host cores expands
-    well above the PCIe rate, which a 64 MB trial decides once per process (16 cores: ~2.5e10 counts/s).
-    With eight ranks on a 32-vCPU box each rank has 4 threads and the host MEMORY system is the limit
-    (profiles/r02_host_bw_8gpu.txt): the rule then keeps "direct".  PST_HOST_TRANSPORT=direct|i32|u16|u8
-    overrides."""
+    """Transport of a host matrix when nothing was asked for.  "direct" / "i32": the counts cross PCIe as
+    int32, 4 B per count (55-57 GB/s = 1.4e10 counts/s for one B200).  "u8": they cross as uint8 + exact
+    overflow list (a quarter of the bytes) and host threads expand them with non-temporal stores
+    (pst_host_widen_stream: 5.7e9 counts/s per thread, 3.4e10 with 16).  Measured: one rank with 16 threads
+    2.4e10 against 1.3e10 counts/s; eight ranks with 4 threads each on a 32-vCPU box, where the host MEMORY
+    system is the limit, 3.0e10 against 2.3e10 (6 B of host traffic per count instead of the 10 B of an
+    expansion with ordinary stores, which lost to "direct" there).  So "u8" wherever the CPU has the streaming
+    stores and this rank has at least 3 threads, or 10 threads without them.  A fixed rule, not a timing trial:
+    every rank of a job must pick the same transport (a trial run by eight ranks at once measured their
+    contention and split them).  PST_HOST_TRANSPORT=direct|i32|u16|u8 overrides."""
     forced = os.environ.get("PST_HOST_TRANSPORT")
     if forced:
         return forced
-    return "u8" if _widen_rate(threads) >= 1.3 * _PCIE_INT32_RATE else "direct"
+    need = 3 if nat.load().pst_host_stream_stores() else 10
+    return "u8" if threads >= need else "direct"
 
 
 def _host_threads():
