@@ -476,6 +476,24 @@ def test_staged_host_transports_and_default_api_are_exact():
     eng.draw_to_host(rows, sc, 9, 77, pinned)                               # int64 tensor: staged too
     assert np.array_equal(pinned.numpy(), want)
     eng.check()
+    # no transport argument: the library's own choice; when that is uint8 and the overflow list does not fit
+    # (forced here by a 10-entry list) the chunk is sampled again through the wide transport - same counts,
+    # and the process keeps to the wide transport from then on
+    from prosstt_b200 import device as pdev
+    state = pdev._AUTO_STATE["narrow_overflowed"]
+    try:
+        for target in (np.full((n, t.G), -1, dtype=np.int64), torch.full((n, t.G), -1, dtype=torch.int32).pin_memory()):
+            pdev._AUTO_STATE["narrow_overflowed"] = False
+            eng.draw_to_host(rows, sc, 9, 77, target, overflow_cap=10)
+            got = target if isinstance(target, np.ndarray) else target.numpy()
+            assert np.array_equal(got, want)
+            if pdev._shared_host_transport(pdev._host_threads()) == "u8":
+                assert pdev._AUTO_STATE["narrow_overflowed"]
+        with pytest.raises(OverflowError):                                  # an explicit request is not second-guessed
+            eng.draw_to_host(rows, sc, 9, 77, np.empty((n, t.G), dtype=np.int64), transport="u8", overflow_cap=10)
+    finally:
+        pdev._AUTO_STATE["narrow_overflowed"] = state
+    eng.check()
     # the public call with the reference's defaults: int64 ndarray, equal to the device-resident result
     kw = dict(alpha=s["alpha"], beta=s["beta"], seed=5, device=DEV)
     X64 = sim.sample_density(t, 3000, **kw)[0]
