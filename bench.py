@@ -221,9 +221,14 @@ def measured_peaks():
     return peak, src, store
 
 
-def profiled_traffic():
+def _profile_file(stem, sampler):
+    """profiles/<stem>.json for the hybrid kernel, profiles/<stem>_<sampler>.json for another sampler's."""
+    return os.path.join(ROOT, "profiles", stem + ("" if sampler == "hybrid" else "_" + sampler) + ".json")
+
+
+def profiled_traffic(sampler="hybrid"):
     """DRAM bytes per count of the draw kernel from the committed ncu capture (NOT measured by this run)."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+    path = _profile_file("traffic", sampler)
     if not os.path.exists(path):
         return None, None
     with open(path) as fh:
@@ -231,10 +236,10 @@ def profiled_traffic():
     return float(rec["bytes_per_count"]), rec.get("source")
 
 
-def issue_bound():
-    """Speed of light of the instruction-bound draw kernel (profiles/issue_bound.json, from the ncu
+def issue_bound(sampler="hybrid"):
+    """Speed of light of the instruction-bound draw kernel (profiles/issue_bound*.json, from the ncu
     capture of the committed kernel): warp-instructions per count and the issue rate of a B200."""
-    path = os.path.join(ROOT, "profiles", "issue_bound.json")
+    path = _profile_file("issue_bound", sampler)
     if not os.path.exists(path):
         return None
     with open(path) as fh:
@@ -405,7 +410,7 @@ def run_ours(a):
     per_launch_cells = mine if not draws else mine / (len(draws) / a.steps)
     algo_bytes = 4.0 * mine * G                            # per step of this rank
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
-    bpc, bpc_src = profiled_traffic()
+    bpc, bpc_src = profiled_traffic(sampler)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None if bpc is None else bpc * per_launch_cells * G,
             "traffic_source": None if bpc is None else "NOT measured by this run: %.3f B/count from %s, scaled to "
@@ -418,7 +423,7 @@ def run_ours(a):
     if store_peak:
         roof["store_only_peak"] = store_peak
         roof["frac_of_store_only_peak"] = achieved / store_peak
-    ib = issue_bound()
+    ib = issue_bound(sampler)
     if ib:
         sol = ib["issue_slots_per_s"] / ib["speed_of_light_warp_inst_per_count"]
         roof["issue_bound"] = {"counts_per_s_at_speed_of_light": sol, "frac": (mine * G / (kernel_ms / 1e3)) / sol,

@@ -373,3 +373,24 @@ def test_result_pool_recycles_only_unreachable_matrices():
             del os.environ["PST_HOST_POOL_GB"]
         else:
             os.environ["PST_HOST_POOL_GB"] = old
+
+
+def test_default_transport_is_a_fixed_rule_of_cpu_and_threads(monkeypatch):
+    """The transport nobody asked for (device.py:_shared_host_transport) must be the same on every rank of a
+    job: a function of the CPU's store instructions and the rank's thread count only, overridable by
+    PST_HOST_TRANSPORT; the thread count is the rank's share of the cores (LOCAL_WORLD_SIZE)."""
+    from prosstt_b200 import device as pdev
+    monkeypatch.delenv("PST_HOST_TRANSPORT", raising=False)
+    streams = bool(nat.load().pst_host_stream_stores())
+    need = 3 if streams else 10
+    assert pdev._shared_host_transport(need) == "u8" and pdev._shared_host_transport(need - 1) == "direct"
+    assert pdev._shared_host_transport(64) == "u8" and pdev._shared_host_transport(1) == "direct"
+    monkeypatch.setenv("PST_HOST_TRANSPORT", "u16")
+    assert pdev._shared_host_transport(1) == "u16" and pdev._shared_host_transport(64) == "u16"
+    cores = len(os.sched_getaffinity(0))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert pdev._host_threads() == cores
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", str(4 * cores))
+    assert pdev._host_threads() == 1
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "not a number")
+    assert pdev._host_threads() == cores
