@@ -12,6 +12,7 @@ a result that has been garbage-collected is kept here and handed out again: same
 Only matrices of at least 4 MiB are pooled; at most PST_HOST_POOL_GB (default: a quarter of the
 physical memory) of free buffers is retained; `release()` returns them to the OS; PST_HOST_POOL_GB=0
 disables the pool (every result is then `np.empty`)."""
+import collections
 import mmap
 import os
 import threading
@@ -21,6 +22,7 @@ import numpy as np
 
 _LOCK = threading.Lock()
 _FREE = []                    # [nbytes, mmap] of results that were garbage-collected, pages mapped
+_RETURNED = collections.deque()   # what finalizers hand back; moved into _FREE under the lock by the next caller
 _MIN_BYTES = 4 << 20
 _HUGE = 2 << 20
 
@@ -39,22 +41,34 @@ def _cap_bytes():
 
 
 def _give_back(buf, size):
+    # runs wherever the last reference dies - possibly inside the garbage collector while this module holds
+    # its lock: only an atomic append here
+    _RETURNED.append([size, buf])
+
+
+def _collect():
+    """Move returned buffers into the free list and enforce the cap (call with _LOCK held)."""
+    while True:
+        try:
+            _FREE.append(_RETURNED.popleft())
+        except IndexError:
+            break
     cap = _cap_bytes()
-    with _LOCK:
-        _FREE.append([size, buf])
-        total = sum(b[0] for b in _FREE)
-        while _FREE and total > cap:                 # oldest first
-            total -= _FREE.pop(0)[0]
+    total = sum(b[0] for b in _FREE)
+    while _FREE and total > cap:                     # oldest first
+        total -= _FREE.pop(0)[0]
 
 
 def release():
     """Return every retained buffer to the OS."""
     with _LOCK:
+        _collect()
         del _FREE[:]
 
 
 def retained_bytes():
     with _LOCK:
+        _collect()
         return sum(b[0] for b in _FREE)
 
 
@@ -71,6 +85,7 @@ def result_array(shape, dtype):
     need = (nbytes + _HUGE - 1) // _HUGE * _HUGE
     buf = None
     with _LOCK:
+        _collect()
         best = None
         for i, (size, _) in enumerate(_FREE):        # smallest retained buffer that fits without wasting half
             if need <= size <= 2 * need and (best is None or size < _FREE[best][0]):
@@ -79,7 +94,8 @@ def result_array(shape, dtype):
             need, buf = _FREE.pop(best)
     fresh = buf is None
     if fresh:
-        buf = mmap.mmap(-1, need)
+        # private like any malloc'ed array: a forked child gets its own copy-on-write view
+        buf = mmap.mmap(-1, need, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
         if hasattr(buf, "madvise") and hasattr(mmap, "MADV_HUGEPAGE"):
             try:
                 buf.madvise(mmap.MADV_HUGEPAGE)

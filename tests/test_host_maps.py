@@ -354,6 +354,12 @@ def test_result_pool_recycles_only_unreachable_matrices():
     assert not fresh and hp.retained_bytes() == 0 and b.shape == (999, 2000)
     c, fresh = hp.result_array((999, 2000), np.int64)              # the first is still alive: new memory
     assert fresh
+    # private memory like np.empty's: what a forked child writes stays in the child
+    pid = os.fork()
+    if pid == 0:
+        b[:] = 9
+        os._exit(0 if int(b[5, 5]) == 9 else 1)
+    assert os.waitpid(pid, 0)[1] == 0 and int(b[5, 5]) == 7
     del b, c
     gc.collect()
     small, fresh = hp.result_array((100, 2000), np.int32)          # far smaller than what is retained: not reused
