@@ -10,7 +10,7 @@ a result that has been garbage-collected is kept here and handed out again: same
 (writeable, C-contiguous, views keep it alive), no page faults from the second call on.
 
 Only matrices of at least 4 MiB are pooled; at most PST_HOST_POOL_GB (default: a quarter of the
-physical memory) of free buffers is retained; `release()` returns them to the OS; PST_HOST_POOL_GB=0
+physical memory, divided among the ranks that share the host) of free buffers is retained; `release()` returns them to the OS; PST_HOST_POOL_GB=0
 disables the pool (every result is then `np.empty`)."""
 import collections
 import mmap
@@ -35,7 +35,11 @@ def _cap_bytes():
         except ValueError:
             return 0
     try:
-        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 4
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))      # ranks of one job share the host
+    except ValueError:
+        ranks = 1
+    try:
+        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // (4 * ranks)
     except (ValueError, OSError, AttributeError):
         return 0
 
