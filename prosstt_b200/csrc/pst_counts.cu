@@ -339,6 +339,9 @@ struct HyWarpQueues {
 #define HY_MIX_ATOMIC 0   // mixture-queue slots: one atomic per lane (1) or ballots (0); measured equal at the bench
                           // depth, ballots better when every count takes the mixture (gamma_poisson sampler)
 #endif
+#ifndef HY_META2
+#define HY_META2 1        // cell metadata of the whole group loaded at the chunk start (1) or every 32 cells in the loop (0)
+#endif
 #ifndef HY_CHUNK_CELLS
 #define HY_CHUNK_CELLS 64                    // most cells per chunk (x 32 quads = 8192 counts); all of one tree row
 #endif
@@ -571,6 +574,24 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
     // (first + l) of the group with one coalesced request per 32 cells and the loop broadcasts it with
     // shuffles.  A library size that is not positive and finite is flagged and sampled as NaN (every
     // count of the cell goes to the mixture queue, whose drain leaves 0).
+#if HY_META2
+    // A group has at most 64 cells: lane l holds the metadata of cells l and 32 + l, both loaded here, so the
+    // cell loop contains no load (the every-32-cells reload used to sit in it as 16 predicated-off instructions)
+    static_assert(HY_CHUNK_CELLS <= 64, "two metadata registers per lane cover a group");
+    int32_t meta_cell, meta_cell_hi; float meta_s, meta_s_hi;
+    auto load_meta = [&](int i, int32_t &mc, float &ms) {
+      mc = order[pos0 + (uint32_t)(i < n_cells ? i : n_cells - 1)];
+      ms = scaling[mc];
+      if (!(ms > 0.f && ms < 3.0e38f)) { flag |= PST_FLAG_DOMAIN; ms = __int_as_float(0x7fc00000); }
+    };
+    load_meta(lane, meta_cell, meta_s);
+    load_meta(32 + lane, meta_cell_hi, meta_s_hi);
+    for (int ci = 0; ci < n_cells; ++ci) {
+      const int src = ci & 31;
+      const bool upper = ci >= 32;
+      const int32_t cell = __shfl_sync(0xffffffffu, upper ? meta_cell_hi : meta_cell, src);
+      const float s = __shfl_sync(0xffffffffu, upper ? meta_s_hi : meta_s, src);
+#else
     int32_t meta_cell = 0; float meta_s = 1.f;
     auto load_meta = [&](int first) {                       // cells first .. first+31 of this group
       const int i = first + lane;
@@ -584,6 +605,7 @@ draw_counts_kernel(const __grid_constant__ PhiloxKey key, const float *__restric
       const int32_t cell = __shfl_sync(0xffffffffu, meta_cell, src);
       const float s = __shfl_sync(0xffffffffu, meta_s, src);
       if (src == 31) load_meta(ci + 1);                     // warp-uniform branch, every 32 cells
+#endif
 
       // ---- this cell's quad
       float t[4], d[4], a[4], q[4], mu[4], th[4];

@@ -1,6 +1,5 @@
 #!/bin/bash
-set -x
 mkdir -p gpurun_out
-python bench.py --sampler gamma_poisson --no-cpu-baseline --e2e-steps 3 > gpurun_out/r_bench_c4_gamma_poisson.json 2> gpurun_out/r_bench.err
-for m in -2 1.5; do echo "== depth $m"; python tools/sampler_bench.py --cells 100000 --samplers gamma_poisson --reps 3 --scale-mean $m 2>&1 | grep -E "^hybrid|^gamma|rror"; done > gpurun_out/r_sampler.txt 2>&1
-tail -n 2 gpurun_out/r_bench.err; cat gpurun_out/r_sampler.txt | cut -c1-120; head -c 600 gpurun_out/r_bench_c4_gamma_poisson.json
+for l in meta1 meta2 meta1 meta2; do echo "== $l depth 0"; PST_LIB=tools/lib_$l.so python tools/sampler_bench.py --cells 200000 --samplers hybrid --reps 3 2>&1 | grep -E "^hybrid|rror"; done > gpurun_out/t_sampler.txt 2>&1
+PST_LIB=tools/lib_meta2.so python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t_pytest.txt
+cat gpurun_out/t_sampler.txt | cut -c1-170; cat gpurun_out/t_pytest.txt
