@@ -190,3 +190,73 @@ def test_ptrs_and_marsaglia_tsang_constants_sample_the_right_distributions():
         g = d * v[ok]
         assert ok.mean() > 0.9
         assert scipy.stats.kstest(g[:100000], scipy.stats.gamma(shape).cdf).pvalue > 1e-4, shape
+
+
+def test_pipeline_queues_never_overflow_and_finish_every_count():
+    """Model of draw_counts_mixture_kernel's queue discipline (capacity read from the CUDA source): per cell
+    iteration a warp appends up to 4 x 32 routed entries, then `run_queues(32)` drains full batches - small-lambda
+    and PTRS first, then ONE batch of gamma retries, repeated - and `run_queues(1)` empties everything at the end.
+    Whatever the mix of outcomes (all small, all PTRS, all rejected, random), no queue ever holds more than its
+    capacity and every count is written exactly once."""
+    src = _source("pst_counts.cu")
+    cap = int(re.search(r"constexpr int MX_CAP = (\d+);", src).group(1))
+    rng = np.random.RandomState(11)
+
+    def simulate(p_reject, p_small, p_ptrs_reject, iterations):
+        fill = {"g": [], "s": [], "l": []}                   # entries: (count id, attempt)
+        high = {"g": 0, "s": 0, "l": 0}
+        written = {}
+        next_id = [0]
+
+        def note():
+            for k in fill:
+                high[k] = max(high[k], len(fill[k]))
+                assert len(fill[k]) <= cap, (k, len(fill[k]))
+
+        def route(entries):                                  # outcome of one gamma attempt per entry
+            for cid, att in entries:
+                if att < 62 and rng.random_sample() < p_reject:
+                    fill["g"].append((cid, att + 1))
+                elif rng.random_sample() < p_small:
+                    fill["s"].append((cid, 0))
+                else:
+                    fill["l"].append((cid, 0))
+            note()
+
+        def take(k, n):
+            batch = fill[k][len(fill[k]) - n:]
+            del fill[k][len(fill[k]) - n:]
+            return batch
+
+        def run_queues(limit):
+            while any(len(fill[k]) >= limit for k in fill):
+                while len(fill["s"]) >= limit:
+                    for cid, _ in take("s", min(32, len(fill["s"]))):
+                        written[cid] = written.get(cid, 0) + 1
+                while len(fill["l"]) >= limit:
+                    for cid, att in take("l", min(32, len(fill["l"]))):
+                        if att < 125 and rng.random_sample() < p_ptrs_reject:
+                            fill["l"].append((cid, att + 1))
+                        else:
+                            written[cid] = written.get(cid, 0) + 1
+                    note()
+                if len(fill["g"]) >= limit:
+                    route(take("g", min(32, len(fill["g"]))))
+
+        for _ in range(iterations):
+            for j in range(4):                               # the four counts of a lane's quad, 32 lanes each
+                ids = list(range(next_id[0], next_id[0] + 32))
+                next_id[0] += 32
+                route([(c, 0) for c in ids])
+            run_queues(32)
+            assert all(len(fill[k]) < 32 for k in fill)      # what the next iteration's 128 appends rely on
+        run_queues(1)
+        assert all(len(fill[k]) == 0 for k in fill)
+        assert len(written) == next_id[0] and set(written.values()) == {1}
+        return high
+
+    assert 31 + 128 < cap + 1                                # 31 carried + 4 x 32 new entries fit
+    for p_reject, p_small, p_ptrs in ((0.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0.0, 0.0, 0.9), (0.95, 0.5, 0.5),
+                                      (0.05, 0.85, 0.12), (0.5, 0.0, 0.5), (1.0, 0.5, 0.0)):
+        high = simulate(p_reject, p_small, p_ptrs, 40)
+        assert max(high.values()) <= 31 + 128, high
