@@ -355,7 +355,10 @@ def test_result_pool_recycles_only_unreachable_matrices():
     c, fresh = hp.result_array((999, 2000), np.int64)              # the first is still alive: new memory
     assert fresh
     # private memory like np.empty's: what a forked child writes stays in the child
-    pid = os.fork()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)        # "multi-threaded process": the child only writes and exits
+        pid = os.fork()
     if pid == 0:
         b[:] = 9
         os._exit(0 if int(b[5, 5]) == 9 else 1)
